@@ -1,0 +1,181 @@
+/* edmd_b200.h — C ABI of the B200-native EDMD force-and-integrate engine.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI
+ * layer: its seam is the C++ class EDMD (5 void methods on Tetrad*, /root/reference
+ * src/edmd.hpp:54-170) driven by Worker::force_Calculation (src/worker.cpp:147-187) and
+ * Master::update_Velocity/update_Coordinate/merge_Vels_n_Crds/generate_Pair_Lists
+ * (src/master.cpp:157-384).  Each entry point below names the reference interface it
+ * replaces.  Signatures use only plain pointers and sizes.
+ *
+ * All calls on one engine must come from one host thread at a time (the reference's
+ * calculate_Random_Terms is not re-entrant either, edmd.cpp:173,179).  The engine copies
+ * what it is given; it never keeps or frees caller memory.
+ *
+ * Every function returns 0 on success and a negative edmd_status on failure;
+ * edmd_last_error() returns a description of the last failure on the calling thread.
+ * There is NO CPU fallback: without a CUDA device edmd_create fails with EDMD_ERR_CUDA.
+ */
+#ifndef EDMD_B200_H
+#define EDMD_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDMD_B200_ABI_VERSION 1
+
+typedef enum {
+    EDMD_OK = 0,
+    EDMD_ERR_ARG = -1,      /* bad argument / call order                              */
+    EDMD_ERR_CUDA = -2,     /* CUDA runtime failure (no device, OOM, launch error)    */
+    EDMD_ERR_STATE = -3,    /* engine not ready for this call (e.g. no pair list yet) */
+    EDMD_ERR_LIMIT = -4     /* input exceeds a documented limit                       */
+} edmd_status;
+
+/* Simulation parameters in INTERNAL units — the eight public fields of class EDMD
+ * (edmd.hpp:60-74) as EDMD::initialise receives them (edmd.cpp:51-60), i.e. after the unit
+ * conversion of IO::read_Cofig (io.cpp:85-91): dt*=20.455, gamma/=20.455, tautp*=20.455,
+ * scaled = 0.002*temperature. */
+typedef struct edmd_params {
+    double dt, gamma, tautp, temperature, scaled, mole_Cutoff, atom_Cutoff, mole_Least;
+} edmd_params;
+
+/* Byte-for-byte the data members of the reference's class Tetrad (tetrad.hpp:36-60) on
+ * LP64: a `Tetrad*` from reference code can be passed as `edmd_tetrad*` unchanged.
+ * eigenvectors is the row-pointer table of Array::allocate_2D_Double_Array
+ * (array.cpp:24-34): eigenvectors[0] is a dense num_Evecs x 3*num_Atoms row-major block. */
+typedef struct edmd_tetrad {
+    int      num_Atoms;
+    int      num_Evecs;
+    double*  avg;           /* [3N] reference structure, xyz interleaved                */
+    double*  masses;        /* [3N] each atom's mass replicated x3 (io.cpp:149-152)     */
+    double*  abq;           /* [3N] (A,B,q) per atom; only q = abq[3i+2] is ever read   */
+    double*  eigenvalues;   /* [num_Evecs]                                              */
+    double** eigenvectors;  /* [num_Evecs][3N]                                          */
+    double*  ED_Forces;     /* [3N+1] last = ED energy                                  */
+    double*  random_Terms;  /* [3N]                                                     */
+    double*  NB_Forces;     /* [3N+2] last two = NB energy, electrostatic energy        */
+    double   temperature;
+    double*  velocities;    /* [3N]                                                     */
+    double*  coordinates;   /* [3N]                                                     */
+} edmd_tetrad;
+
+typedef struct edmd_engine edmd_engine;
+
+const char* edmd_last_error(void);
+int         edmd_abi_version(void);
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* Replaces EDMD::EDMD + EDMD::initialise (edmd.cpp:23-60).  `device` is the CUDA ordinal. */
+int  edmd_create(const edmd_params* p, int device, edmd_engine** out);
+void edmd_destroy(edmd_engine* e);
+int  edmd_set_params(edmd_engine* e, const edmd_params* p);
+/* krep / qfac are literals in the reference (edmd.cpp:237,242: 100.0, 0.0).  Exposed so
+ * that electrostatics can be switched on (qfac = 332.064/4 per the comment at :240). */
+int  edmd_set_nb_consts(edmd_engine* e, double krep, double qfac);
+
+/* ---- data in / out ----------------------------------------------------------------- */
+/* Replaces Master::send_Tetrads / Worker::recv_Tetrads (master.cpp:137-153, MPI_Tetrad
+ * datatype mpilib.cpp:23-62): uploads avg, masses, abq, eigenvalues, eigenvectors of n
+ * tetrads plus their coordinates and velocities.  Identical parameter sets (same bytes)
+ * are stored once on the device.  bp_atoms (n+3 entries, the per-base-pair atom counts of
+ * the .crd file, io.cpp:201-205) is needed only by edmd_merge and may be NULL. */
+int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const int* bp_atoms);
+/* coordinates + velocities host -> device / device -> host (MPI_Crds, mpilib.cpp:106-130) */
+int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n);
+int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n);
+/* Fills ED_Forces[3N+1], random_Terms[3N], NB_Forces[3N+2] and temperature exactly as the
+ * reference lays them out (MPI_ED_Forces, mpilib.cpp:74-94; master.cpp:308,316-317). */
+int edmd_get_forces(edmd_engine* e, edmd_tetrad* tets, int n);
+/* Overwrites the device force arrays (used to test update_Velocities in isolation). */
+int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n);
+
+/* Flat variants for callers that do not hold Tetrad structs: arrays are tetrad-
+ * concatenated xyz-interleaved, tetrad t at 3*sum_{s<t} num_Atoms[s].  NULL = skip. */
+int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel);
+int edmd_get_state_flat(edmd_engine* e, double* crd, double* vel);
+int edmd_get_forces_flat(edmd_engine* e, double* ed, double* ed_energy, double* rnd,
+                         double* nb, double* nb_energy /* 2 per tetrad */, double* temperature);
+
+/* ---- pair list --------------------------------------------------------------------- */
+/* Replaces Master::cal_Centre_of_Mass + generate_Pair_Lists (master.cpp:157-210): same
+ * inclusion predicate, same (t1,t2) orientation, same order; 64-bit count. */
+int edmd_build_pairlist(edmd_engine* e, long long* num_pairs);
+int edmd_get_pairlist(edmd_engine* e, int* pairs /* 2*num_pairs */, long long cap_pairs);
+/* Install a caller-made list (tests, custom schedules). */
+int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long num_pairs);
+/* Multi-GPU: restrict this engine's NB distance pass to pairs [p0,p1) of the list and its
+ * per-tetrad work (ED, accumulate, integrate, merge output) to tetrads [t0,t1).
+ * Defaults: everything. */
+int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1);
+
+/* ---- the five EDMD methods, batched over all (owned) tetrads ---------------------------- */
+/* EDMD::calculate_ED_Forces (edmd.cpp:64-166) incl. CalcRMSDRotationalMatrix
+ * (qcprot.c:392-407).  Overwrites coordinates with the re-embedded ones, like the reference. */
+int edmd_ed_forces(edmd_engine* e);
+/* EDMD::calculate_Random_Terms (edmd.cpp:170-228).  mode 0: zero terms ("random off").
+ * mode 1: the reference stream — glibc TYPE_3 rand() seeded per call with
+ * (unsigned)(13579 + calls + rank^3 + time0), call counter advancing one per tetrad with
+ * the wrap of edmd.cpp:180, Kinderman-Monahan ratio of uniforms (ACM 712). */
+int edmd_random_terms(edmd_engine* e, int mode, long time0, int rank, long calls_before);
+/* Worker::force_Calculation NB section + Master::process_NB_Forces (worker.cpp:165-179,
+ * master.cpp:297-322): EDMD::calculate_NB_Forces (edmd.cpp:232-285) over the pair list,
+ * per-tetrad sums in pair-list order, then clip of force components to [-1,1]. */
+int edmd_nb_forces(edmd_engine* e);
+/* The two halves of edmd_nb_forces, for multi-GPU drivers: distance pass over this
+ * engine's pair shard (fills the per-pair hit flags), then accumulate + clip on owners. */
+int edmd_nb_scan(edmd_engine* e);
+int edmd_nb_accumulate(edmd_engine* e);
+/* EDMD::update_Velocities (edmd.cpp:289-317) and EDMD::update_Coordinates (:322-327). */
+int edmd_update_velocities(edmd_engine* e);
+int edmd_update_coordinates(edmd_engine* e);
+/* Master::merge_Vels_n_Crds (master.cpp:347-384). */
+int edmd_merge(edmd_engine* e);
+/* Master::write_Info sums (master.cpp:388-401): {sum E_ed, sum E_nb, sum E_el, mean T}. */
+int edmd_get_energies(edmd_engine* e, double out[4]);
+
+/* ---- fused step -------------------------------------------------------------------- */
+/* nsteps x { calculate_Forces; update_Velocity; update_Coordinate } (simulation.cpp:42-48)
+ * with W = 1 semantics.  random_mode as in edmd_random_terms; the call counter continues
+ * from the value passed to edmd_set_rng. */
+int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before);
+int edmd_step(edmd_engine* e, int nsteps, int random_mode);
+int edmd_sync(edmd_engine* e);
+
+/* ---- introspection (bench / multi-GPU plumbing) -------------------------------------- */
+typedef enum {
+    EDMD_BUF_CRD = 0,      /* double [n][3][S]   coordinates, SoA planes per tetrad */
+    EDMD_BUF_VEL = 1,
+    EDMD_BUF_FED = 2,
+    EDMD_BUF_RND = 3,
+    EDMD_BUF_FNB = 4,
+    EDMD_BUF_HIT = 5,      /* unsigned char [num_pairs] per-pair hit flags           */
+    EDMD_BUF_CENTROID = 6  /* double [n][4]                                          */
+} edmd_buffer;
+/* Device pointer + byte size of an engine buffer (for NCCL collectives issued by the
+ * host-side driver through torch.distributed).  Valid until the next upload. */
+int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes);
+int edmd_atom_stride(edmd_engine* e);      /* S: atoms per tetrad plane, multiple of 32   */
+int edmd_num_tetrads(edmd_engine* e);
+long long edmd_num_pairs(edmd_engine* e);
+void* edmd_stream(edmd_engine* e);         /* the cudaStream_t all engine work runs on    */
+/* Average device time (ms) per launch of each kernel since the last reset, measured with
+ * CUDA events on the engine stream.  which: 0 ED, 1 NB scan, 2 NB accumulate+integrate,
+ * 3 random, 4 merge, 5 pair list. */
+int edmd_timing_enable(edmd_engine* e, int on);
+int edmd_timing_get(edmd_engine* e, int which, double* total_ms, long long* launches);
+int edmd_timing_reset(edmd_engine* e);
+long long edmd_launch_count(edmd_engine* e);   /* kernels launched since create */
+/* Atom pairs inside atom_Cutoff / tetrad pairs flagged, from the last NB pass. */
+int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs);
+
+/* FP64 peak of this device measured with a dependent-free DFMA loop (the roofline
+ * denominator for the NB kernel; MEASURED_PEAKS.json has no FP64 entry). */
+int edmd_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDMD_B200_H */

@@ -1,0 +1,821 @@
+// engine.cu — the C ABI (include/edmd_b200.h) over the sm_100a kernels.
+//
+// Host-side replacement for the reference's orchestration of the hot path: Master/Worker
+// message protocol (/root/reference/src/master.cpp:268-343, src/worker.cpp:147-199) becomes
+// in-order kernel launches on one CUDA stream; MPI derived datatypes (src/mpilib.cpp) become
+// device-resident SoA planes.  No CPU fallback exists: every compute entry point launches
+// CUDA kernels or fails.
+#include "../../include/edmd_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace edmd;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess)                                                            \
+            return fail(EDMD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+enum TimerId { T_ED = 0, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT, T_COUNT };
+
+struct Timer {
+    std::vector<cudaEvent_t> ev;   // start/stop pairs not yet folded
+    double total_ms = 0.0;
+    long long launches = 0;
+};
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+}  // namespace
+
+struct edmd_engine {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t st = nullptr;
+    SimParams sp{};
+
+    int n = 0, S = 0, P = 0, NEV = 0;
+    long long total3 = 0;
+    std::vector<int> natoms_h, nev_h, param_id_h;
+    std::vector<long long> off3_h;
+
+    // device: metadata + parameter sets
+    int *d_natoms = nullptr, *d_param_id = nullptr, *d_ps_na = nullptr, *d_ps_nev = nullptr;
+    long long* d_off3 = nullptr;
+    double *d_avg = nullptr, *d_mass = nullptr, *d_chg = nullptr, *d_eval = nullptr, *d_evec = nullptr;
+    ParamSets ps{};
+
+    // device: state planes
+    double *crd = nullptr, *vel = nullptr, *fed = nullptr, *rnd = nullptr, *fnb = nullptr;
+    double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr;
+    bool rnd_zero = true;   // random terms currently all zero
+
+    // staging (interleaved flat), 3 slots
+    double* d_stage = nullptr;
+    double* h_stage = nullptr;   // pinned
+
+    // pair list + adjacency
+    int2* d_pairs = nullptr;
+    long long np = 0, pairs_cap = 0;
+    unsigned char* d_hit = nullptr;
+    long long *d_row_count = nullptr, *d_row_off = nullptr, *d_adj_off = nullptr;
+    int *d_adj_partner = nullptr, *d_adj_pair = nullptr;
+    long long adj_cap = 0;
+    bool have_pairs = false;
+    bool hits_valid = false;
+
+    // merge
+    int* d_bp_off = nullptr;
+    bool have_bp = false;
+
+    // shard
+    int t0 = 0, t1 = 0;
+    long long p0 = 0, p1 = 0;
+    bool shard_pairs_custom = false;
+
+    // rng stream position
+    long time0 = 1000000000L;
+    int rank = 1;
+    long calls = 0;
+
+    int scan_grid = 592;
+    bool timing = false;
+    Timer timers[T_COUNT];
+    long long launches = 0;
+};
+
+namespace {
+
+void timer_begin(edmd_engine* e, int id) {
+    if (!e->timing) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, e->st);
+    e->timers[id].ev.push_back(a);
+    e->timers[id].ev.push_back(b);
+}
+void timer_end(edmd_engine* e, int id, int launches) {
+    e->launches += launches;
+    if (!e->timing) return;
+    Timer& t = e->timers[id];
+    cudaEventRecord(t.ev.back(), e->st);
+    t.launches += launches;
+}
+void timer_fold(edmd_engine* e, int id) {
+    Timer& t = e->timers[id];
+    if (t.ev.empty()) return;
+    cudaStreamSynchronize(e->st);
+    for (size_t i = 0; i + 1 < t.ev.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.ev[i], t.ev[i + 1]) == cudaSuccess) t.total_ms += ms;
+        cudaEventDestroy(t.ev[i]); cudaEventDestroy(t.ev[i + 1]);
+    }
+    t.ev.clear();
+}
+
+void free_system(edmd_engine* e) {
+    cudaFree(e->d_natoms); cudaFree(e->d_param_id); cudaFree(e->d_ps_na); cudaFree(e->d_ps_nev);
+    cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
+    cudaFree(e->d_eval); cudaFree(e->d_evec);
+    cudaFree(e->crd); cudaFree(e->vel); cudaFree(e->fed); cudaFree(e->rnd); cudaFree(e->fnb);
+    cudaFree(e->e_ed); cudaFree(e->e_nb); cudaFree(e->temp); cudaFree(e->cen);
+    cudaFree(e->d_stage); if (e->h_stage) cudaFreeHost(e->h_stage);
+    cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_row_count); cudaFree(e->d_row_off);
+    cudaFree(e->d_adj_off); cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair); cudaFree(e->d_bp_off);
+    e->d_natoms = e->d_param_id = e->d_ps_na = e->d_ps_nev = nullptr; e->d_off3 = nullptr;
+    e->d_avg = e->d_mass = e->d_chg = e->d_eval = e->d_evec = nullptr;
+    e->crd = e->vel = e->fed = e->rnd = e->fnb = e->e_ed = e->e_nb = e->temp = e->cen = nullptr;
+    e->d_stage = nullptr; e->h_stage = nullptr;
+    e->d_pairs = nullptr; e->d_hit = nullptr; e->d_row_count = e->d_row_off = e->d_adj_off = nullptr;
+    e->d_adj_partner = e->d_adj_pair = nullptr; e->d_bp_off = nullptr;
+    e->np = e->pairs_cap = e->adj_cap = 0; e->have_pairs = e->hits_valid = e->have_bp = false;
+    e->n = 0;
+}
+
+uint64_t hash_bytes(uint64_t h, const void* p, size_t bytes) {
+    const uint64_t* w = (const uint64_t*)p;
+    for (size_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 0x100000001b3ULL; h ^= h >> 29; }
+    return h;
+}
+
+struct PtrKey {
+    const void *a, *m, *q, *l, *v; int na, nev;
+    bool operator==(const PtrKey& o) const {
+        return a == o.a && m == o.m && q == o.q && l == o.l && v == o.v && na == o.na && nev == o.nev;
+    }
+};
+struct PtrKeyHash {
+    size_t operator()(const PtrKey& k) const {
+        return (size_t)((uintptr_t)k.a * 31 + (uintptr_t)k.v * 17 + (uintptr_t)k.m * 7 + (uintptr_t)k.l + k.na);
+    }
+};
+
+int ensure_pair_capacity(edmd_engine* e, long long np) {
+    if (np <= e->pairs_cap) return 0;
+    long long cap = std::max(np, e->pairs_cap * 3 / 2 + 1024);
+    cudaFree(e->d_pairs); cudaFree(e->d_hit);
+    e->d_pairs = nullptr; e->d_hit = nullptr; e->pairs_cap = 0;
+    CK(dev_alloc(&e->d_pairs, (size_t)cap));
+    CK(dev_alloc(&e->d_hit, (size_t)cap));
+    e->pairs_cap = cap;
+    return 0;
+}
+
+// CSR over tetrads of the pair list, entries in pair-list order (worker.cpp:166-179 accumulates
+// in that order).  Host-side: runs every ntsync steps only.
+int build_adjacency(edmd_engine* e, const std::vector<int2>& pairs) {
+    const int n = e->n;
+    const long long np = (long long)pairs.size();
+    std::vector<long long> off(n + 1, 0);
+    for (long long p = 0; p < np; p++) { off[pairs[p].x + 1]++; off[pairs[p].y + 1]++; }
+    for (int t = 0; t < n; t++) off[t + 1] += off[t];
+    std::vector<int> partner((size_t)(2 * np) + 1), pidx((size_t)(2 * np) + 1);
+    std::vector<long long> cur(off.begin(), off.end() - 1);
+    for (long long p = 0; p < np; p++) {
+        const int a = pairs[p].x, b = pairs[p].y;
+        partner[cur[a]] = b;                       pidx[cur[a]++] = (int)p;
+        partner[cur[b]] = a | (int)0x80000000;     pidx[cur[b]++] = (int)p;
+    }
+    if (2 * np > e->adj_cap) {
+        cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair);
+        e->d_adj_partner = e->d_adj_pair = nullptr; e->adj_cap = 0;
+        const long long cap = 2 * np + 1024;
+        CK(dev_alloc(&e->d_adj_partner, (size_t)cap));
+        CK(dev_alloc(&e->d_adj_pair, (size_t)cap));
+        e->adj_cap = cap;
+    }
+    CK(cudaMemcpyAsync(e->d_adj_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
+    if (np) {
+        CK(cudaMemcpyAsync(e->d_adj_partner, partner.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice, e->st));
+        CK(cudaMemcpyAsync(e->d_adj_pair, pidx.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice, e->st));
+    }
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int check_ready(edmd_engine* e, bool need_pairs) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    if (e->n == 0) return fail(EDMD_ERR_STATE, "no tetrads uploaded (call edmd_upload_tetrads first)");
+    if (need_pairs && !e->have_pairs)
+        return fail(EDMD_ERR_STATE, "no pair list (call edmd_build_pairlist or edmd_set_pairlist first)");
+    return 0;
+}
+
+int do_ed(edmd_engine* e) {
+    timer_begin(e, T_ED);
+    CK(launch_ed_forces(e->ps, e->d_param_id, e->crd, e->fed, e->e_ed, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
+    timer_end(e, T_ED, 1);
+    return 0;
+}
+int do_scan(edmd_engine* e) {
+    timer_begin(e, T_SCAN);
+    CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, e->d_hit, e->p0, e->p1, e->S,
+                      nb_effective_cut2(e->sp), e->scan_grid, e->st));
+    timer_end(e, T_SCAN, e->p1 > e->p0 ? 1 : 0);
+    e->hits_valid = true;
+    return 0;
+}
+int do_accumulate(edmd_engine* e, int use_hits) {
+    timer_begin(e, T_ACC);
+    CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off,
+                            e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
+                            e->sp, use_hits, e->st));
+    timer_end(e, T_ACC, 1);
+    return 0;
+}
+int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before) {
+    if (mode == 0) {
+        if (!e->rnd_zero) {
+            CK(cudaMemsetAsync(e->rnd, 0, sizeof(double) * (size_t)e->n * 3 * e->S, e->st));
+            e->rnd_zero = true;
+        }
+        return 0;
+    }
+    if (mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown (0 = off, 1 = reference stream)", mode);
+    timer_begin(e, T_RNG);
+    CK(launch_random_terms(e->ps, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
+                           calls_before + e->t0, e->st));
+    timer_end(e, T_RNG, 1);
+    e->rnd_zero = false;
+    return 0;
+}
+int do_integrate(edmd_engine* e, int do_vel, int do_crd) {
+    timer_begin(e, T_INT);
+    CK(launch_integrate(e->ps, e->d_param_id, e->vel, e->crd, e->fed, e->rnd_zero ? nullptr : e->rnd, e->fnb,
+                        e->temp, e->t0, e->t1 - e->t0, do_vel, do_crd, e->sp, e->st));
+    timer_end(e, T_INT, 1);
+    return 0;
+}
+
+// planes -> interleaved flat on the device (slot of d_stage), then to the pinned slot
+int stage_out(edmd_engine* e, const double* planes, int slot) {
+    double* d = e->d_stage + (size_t)slot * e->total3;
+    CK(launch_unpack_planes(planes, e->d_off3, e->d_natoms, d, e->n, e->S, e->st));
+    e->launches++;
+    CK(cudaMemcpyAsync(e->h_stage + (size_t)slot * e->total3, d, sizeof(double) * e->total3,
+                       cudaMemcpyDeviceToHost, e->st));
+    return 0;
+}
+int stage_in(edmd_engine* e, double* planes, int slot) {
+    double* d = e->d_stage + (size_t)slot * e->total3;
+    CK(cudaMemcpyAsync(d, e->h_stage + (size_t)slot * e->total3, sizeof(double) * e->total3,
+                       cudaMemcpyHostToDevice, e->st));
+    CK(launch_pack_planes(d, e->d_off3, e->d_natoms, planes, e->n, e->S, e->st));
+    e->launches++;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* edmd_last_error(void) { return g_err.c_str(); }
+int edmd_abi_version(void) { return EDMD_B200_ABI_VERSION; }
+
+int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
+    if (!out) return fail(EDMD_ERR_ARG, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(EDMD_ERR_CUDA, "no CUDA device available (%s); this engine has no CPU fallback",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "device count 0");
+    if (device < 0 || device >= count) return fail(EDMD_ERR_ARG, "device %d out of range [0,%d)", device, count);
+    CK(cudaSetDevice(device));
+    edmd_engine* e = new edmd_engine();
+    e->device = device;
+    cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    // EDMD::EDMD defaults (edmd.cpp:23-43)
+    e->sp = SimParams{0.002 * 20.455, 2.0 / 20.455, 0.2 * 20.455, 300.0, 0.002 * 300.0, 30.0, 10.0, 5.0, 100.0, 0.0};
+    if (p) {
+        e->sp.dt = p->dt; e->sp.gamma = p->gamma; e->sp.tautp = p->tautp; e->sp.temperature = p->temperature;
+        e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
+        e->sp.mole_least = p->mole_Least;
+    }
+    e->scan_grid = e->sms * 4;
+    *out = e;
+    return 0;
+}
+
+void edmd_destroy(edmd_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    for (int i = 0; i < T_COUNT; i++) timer_fold(e, i);
+    free_system(e);
+    if (e->st) cudaStreamDestroy(e->st);
+    delete e;
+}
+
+int edmd_set_params(edmd_engine* e, const edmd_params* p) {
+    if (!e || !p) return fail(EDMD_ERR_ARG, "null argument");
+    e->sp.dt = p->dt; e->sp.gamma = p->gamma; e->sp.tautp = p->tautp; e->sp.temperature = p->temperature;
+    e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
+    e->sp.mole_least = p->mole_Least;
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_set_nb_consts(edmd_engine* e, double krep, double qfac) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->sp.krep = krep; e->sp.qfac = qfac;
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const int* bp_atoms) {
+    if (!e || !tets || n <= 0) return fail(EDMD_ERR_ARG, "bad arguments to edmd_upload_tetrads");
+    CK(cudaSetDevice(e->device));
+    free_system(e);
+
+    int max_atoms = 0, max_nev = 0;
+    for (int t = 0; t < n; t++) {
+        if (tets[t].num_Atoms <= 0 || tets[t].num_Evecs < 0) return fail(EDMD_ERR_ARG, "tetrad %d: bad sizes", t);
+        max_atoms = std::max(max_atoms, tets[t].num_Atoms);
+        max_nev = std::max(max_nev, tets[t].num_Evecs);
+    }
+    const int S = (max_atoms + 31) & ~31;
+    if (S > kMaxStride)
+        return fail(EDMD_ERR_LIMIT, "tetrad with %d atoms exceeds the engine limit of %d atoms per tetrad",
+                    max_atoms, kMaxStride);
+    if (max_nev > 64) return fail(EDMD_ERR_LIMIT, "%d eigenvectors exceeds the engine limit of 64", max_nev);
+    const int NEV = std::max(max_nev, 1);
+
+    // de-duplicate parameter sets: pointer identity first, then content
+    std::unordered_map<PtrKey, int, PtrKeyHash> by_ptr;
+    std::unordered_map<uint64_t, std::vector<int> > by_hash;   // hash -> parameter-set ids
+    std::vector<int> rep;                                       // representative tetrad of each set
+    e->param_id_h.assign(n, 0); e->natoms_h.assign(n, 0); e->nev_h.assign(n, 0);
+    e->off3_h.assign(n + 1, 0);
+    for (int t = 0; t < n; t++) {
+        const edmd_tetrad& T = tets[t];
+        e->natoms_h[t] = T.num_Atoms; e->nev_h[t] = T.num_Evecs;
+        e->off3_h[t + 1] = e->off3_h[t] + 3LL * T.num_Atoms;
+        const double* evec0 = T.num_Evecs ? T.eigenvectors[0] : nullptr;
+        PtrKey pk{T.avg, T.masses, T.abq, T.eigenvalues, evec0, T.num_Atoms, T.num_Evecs};
+        auto it = by_ptr.find(pk);
+        if (it != by_ptr.end()) { e->param_id_h[t] = it->second; continue; }
+        const size_t b3 = sizeof(double) * 3 * T.num_Atoms;
+        uint64_t h = 0xcbf29ce484222325ULL ^ ((uint64_t)T.num_Atoms << 32) ^ (uint64_t)T.num_Evecs;
+        h = hash_bytes(h, T.avg, b3); h = hash_bytes(h, T.masses, b3); h = hash_bytes(h, T.abq, b3);
+        h = hash_bytes(h, T.eigenvalues, sizeof(double) * T.num_Evecs);
+        if (evec0) h = hash_bytes(h, evec0, b3 * T.num_Evecs);
+        int found = -1;
+        for (int cand : by_hash[h]) {
+            const edmd_tetrad& R = tets[rep[cand]];
+            if (R.num_Atoms == T.num_Atoms && R.num_Evecs == T.num_Evecs && !memcmp(R.avg, T.avg, b3) &&
+                !memcmp(R.masses, T.masses, b3) && !memcmp(R.abq, T.abq, b3) &&
+                !memcmp(R.eigenvalues, T.eigenvalues, sizeof(double) * T.num_Evecs) &&
+                (!evec0 || !memcmp(R.eigenvectors[0], evec0, b3 * T.num_Evecs))) { found = cand; break; }
+        }
+        if (found < 0) { found = (int)rep.size(); rep.push_back(t); by_hash[h].push_back(found); }
+        by_ptr[pk] = found;
+        e->param_id_h[t] = found;
+    }
+    const int P = (int)rep.size();
+    e->n = n; e->S = S; e->P = P; e->NEV = NEV; e->total3 = e->off3_h[n];
+
+    // parameter sets -> plane layout
+    std::vector<int> ps_na(P), ps_nev(P);
+    std::vector<double> avg((size_t)P * 3 * S, 0.0), mass((size_t)P * 3 * S, 1.0), chg((size_t)P * S, 0.0);
+    std::vector<double> eval((size_t)P * NEV, 1.0), evec((size_t)P * NEV * 3 * S, 0.0);
+    for (int p = 0; p < P; p++) {
+        const edmd_tetrad& T = tets[rep[p]];
+        ps_na[p] = T.num_Atoms; ps_nev[p] = T.num_Evecs;
+        for (int a = 0; a < T.num_Atoms; a++) {
+            for (int c = 0; c < 3; c++) {
+                avg[((size_t)p * 3 + c) * S + a] = T.avg[3 * a + c];
+                mass[((size_t)p * 3 + c) * S + a] = T.masses[3 * a + c];
+            }
+            chg[(size_t)p * S + a] = T.abq[3 * a + 2];
+        }
+        for (int j = 0; j < T.num_Evecs; j++) {
+            eval[(size_t)p * NEV + j] = T.eigenvalues[j];
+            const double* row = T.eigenvectors[0] + (size_t)j * 3 * T.num_Atoms;
+            for (int a = 0; a < T.num_Atoms; a++)
+                for (int c = 0; c < 3; c++) evec[(((size_t)p * NEV + j) * 3 + c) * S + a] = row[3 * a + c];
+        }
+    }
+
+    CK(dev_alloc(&e->d_natoms, n)); CK(dev_alloc(&e->d_param_id, n)); CK(dev_alloc(&e->d_off3, n + 1));
+    CK(dev_alloc(&e->d_ps_na, P)); CK(dev_alloc(&e->d_ps_nev, P));
+    CK(dev_alloc(&e->d_avg, avg.size())); CK(dev_alloc(&e->d_mass, mass.size())); CK(dev_alloc(&e->d_chg, chg.size()));
+    CK(dev_alloc(&e->d_eval, eval.size())); CK(dev_alloc(&e->d_evec, evec.size()));
+    const size_t planes = (size_t)n * 3 * S;
+    CK(dev_alloc(&e->crd, planes)); CK(dev_alloc(&e->vel, planes)); CK(dev_alloc(&e->fed, planes));
+    CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
+    CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
+    CK(dev_alloc(&e->cen, 4 * (size_t)n));
+    CK(dev_alloc(&e->d_stage, 3 * (size_t)e->total3));
+    CK(cudaMallocHost((void**)&e->h_stage, sizeof(double) * 3 * (size_t)e->total3));
+    CK(dev_alloc(&e->d_row_count, n)); CK(dev_alloc(&e->d_row_off, n + 1)); CK(dev_alloc(&e->d_adj_off, n + 1));
+
+    CK(cudaMemcpyAsync(e->d_natoms, e->natoms_h.data(), sizeof(int) * n, cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_param_id, e->param_id_h.data(), sizeof(int) * n, cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_off3, e->off3_h.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_ps_na, ps_na.data(), sizeof(int) * P, cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_ps_nev, ps_nev.data(), sizeof(int) * P, cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_avg, avg.data(), sizeof(double) * avg.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_mass, mass.data(), sizeof(double) * mass.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_chg, chg.data(), sizeof(double) * chg.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_eval, eval.data(), sizeof(double) * eval.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaMemcpyAsync(e->d_evec, evec.data(), sizeof(double) * evec.size(), cudaMemcpyHostToDevice, e->st));
+    for (double* buf : {e->vel, e->fed, e->rnd, e->fnb})
+        CK(cudaMemsetAsync(buf, 0, sizeof(double) * planes, e->st));
+    CK(cudaMemsetAsync(e->e_ed, 0, sizeof(double) * n, e->st));
+    CK(cudaMemsetAsync(e->e_nb, 0, sizeof(double) * 2 * n, e->st));
+    CK(cudaMemsetAsync(e->temp, 0, sizeof(double) * n, e->st));
+    CK(cudaStreamSynchronize(e->st));   // host vectors go out of scope
+    e->rnd_zero = true;
+
+    e->ps = ParamSets{e->d_ps_na, e->d_ps_nev, e->d_avg, e->d_mass, e->d_chg, e->d_eval, e->d_evec, S, NEV};
+    e->t0 = 0; e->t1 = n; e->p0 = e->p1 = 0; e->shard_pairs_custom = false;
+
+    if (bp_atoms) {
+        std::vector<int> off(n + 4, 0);
+        for (int b = 0; b < n + 3; b++) off[b + 1] = off[b] + bp_atoms[b];
+        for (int t = 0; t < n; t++)
+            if (off[t + 4] - off[t] != e->natoms_h[t])
+                return fail(EDMD_ERR_ARG, "bp_atoms does not match tetrad %d: %d atoms vs %d (io.cpp:267-269)",
+                            t, off[t + 4] - off[t], e->natoms_h[t]);
+        CK(dev_alloc(&e->d_bp_off, n + 4));
+        CK(cudaMemcpy(e->d_bp_off, off.data(), sizeof(int) * (n + 4), cudaMemcpyHostToDevice));
+        e->have_bp = true;
+    }
+    return edmd_set_state(e, tets, n);
+}
+
+int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_state: n=%d but engine holds %d tetrads", n, e->n);
+    CK(cudaSetDevice(e->device));
+    for (int t = 0; t < n; t++) {
+        const size_t b = sizeof(double) * 3 * e->natoms_h[t];
+        memcpy(e->h_stage + e->off3_h[t], tets[t].coordinates, b);
+        memcpy(e->h_stage + e->total3 + e->off3_h[t], tets[t].velocities, b);
+    }
+    timer_begin(e, T_LAYOUT);
+    if (int rc = stage_in(e, e->crd, 0)) return rc;
+    if (int rc = stage_in(e, e->vel, 1)) return rc;
+    timer_end(e, T_LAYOUT, 0);
+    CK(cudaStreamSynchronize(e->st));
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_state: n mismatch");
+    CK(cudaSetDevice(e->device));
+    if (int rc = stage_out(e, e->crd, 0)) return rc;
+    if (int rc = stage_out(e, e->vel, 1)) return rc;
+    CK(cudaStreamSynchronize(e->st));
+    for (int t = 0; t < n; t++) {
+        const size_t b = sizeof(double) * 3 * e->natoms_h[t];
+        memcpy(tets[t].coordinates, e->h_stage + e->off3_h[t], b);
+        memcpy(tets[t].velocities, e->h_stage + e->total3 + e->off3_h[t], b);
+    }
+    return 0;
+}
+
+int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    if (crd) { memcpy(e->h_stage, crd, sizeof(double) * e->total3); if (int rc = stage_in(e, e->crd, 0)) return rc; }
+    if (vel) { memcpy(e->h_stage + e->total3, vel, sizeof(double) * e->total3); if (int rc = stage_in(e, e->vel, 1)) return rc; }
+    CK(cudaStreamSynchronize(e->st));
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_get_state_flat(edmd_engine* e, double* crd, double* vel) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    if (crd) if (int rc = stage_out(e, e->crd, 0)) return rc;
+    if (vel) if (int rc = stage_out(e, e->vel, 1)) return rc;
+    CK(cudaStreamSynchronize(e->st));
+    if (crd) memcpy(crd, e->h_stage, sizeof(double) * e->total3);
+    if (vel) memcpy(vel, e->h_stage + e->total3, sizeof(double) * e->total3);
+    return 0;
+}
+
+int edmd_get_forces_flat(edmd_engine* e, double* ed, double* ed_energy, double* rnd, double* nb,
+                         double* nb_energy, double* temperature) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    if (ed) if (int rc = stage_out(e, e->fed, 0)) return rc;
+    if (rnd) if (int rc = stage_out(e, e->rnd, 1)) return rc;
+    if (nb) if (int rc = stage_out(e, e->fnb, 2)) return rc;
+    if (ed_energy) CK(cudaMemcpyAsync(ed_energy, e->e_ed, sizeof(double) * e->n, cudaMemcpyDeviceToHost, e->st));
+    if (nb_energy) CK(cudaMemcpyAsync(nb_energy, e->e_nb, sizeof(double) * 2 * e->n, cudaMemcpyDeviceToHost, e->st));
+    if (temperature) CK(cudaMemcpyAsync(temperature, e->temp, sizeof(double) * e->n, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    if (ed) memcpy(ed, e->h_stage, sizeof(double) * e->total3);
+    if (rnd) memcpy(rnd, e->h_stage + e->total3, sizeof(double) * e->total3);
+    if (nb) memcpy(nb, e->h_stage + 2 * e->total3, sizeof(double) * e->total3);
+    return 0;
+}
+
+int edmd_get_forces(edmd_engine* e, edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_forces: n mismatch");
+    std::vector<double> eed(n), enb(2 * (size_t)n), tmp(n);
+    std::vector<double> ed(e->total3), rn(e->total3), nb(e->total3);
+    if (int rc = edmd_get_forces_flat(e, ed.data(), eed.data(), rn.data(), nb.data(), enb.data(), tmp.data())) return rc;
+    for (int t = 0; t < n; t++) {
+        const int n3 = 3 * e->natoms_h[t];
+        const long long o = e->off3_h[t];
+        memcpy(tets[t].ED_Forces, ed.data() + o, sizeof(double) * n3);
+        tets[t].ED_Forces[n3] = eed[t];
+        memcpy(tets[t].random_Terms, rn.data() + o, sizeof(double) * n3);
+        memcpy(tets[t].NB_Forces, nb.data() + o, sizeof(double) * n3);
+        tets[t].NB_Forces[n3] = enb[2 * (size_t)t];
+        tets[t].NB_Forces[n3 + 1] = enb[2 * (size_t)t + 1];
+        tets[t].temperature = tmp[t];
+    }
+    return 0;
+}
+
+int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_forces: n mismatch");
+    CK(cudaSetDevice(e->device));
+    for (int t = 0; t < n; t++) {
+        const size_t b = sizeof(double) * 3 * e->natoms_h[t];
+        memcpy(e->h_stage + e->off3_h[t], tets[t].ED_Forces, b);
+        memcpy(e->h_stage + e->total3 + e->off3_h[t], tets[t].random_Terms, b);
+        memcpy(e->h_stage + 2 * e->total3 + e->off3_h[t], tets[t].NB_Forces, b);
+    }
+    if (int rc = stage_in(e, e->fed, 0)) return rc;
+    if (int rc = stage_in(e, e->rnd, 1)) return rc;
+    if (int rc = stage_in(e, e->fnb, 2)) return rc;
+    CK(cudaStreamSynchronize(e->st));
+    e->rnd_zero = false;
+    return 0;
+}
+
+int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    const int n = e->n;
+    const double cut2 = e->sp.mole_cutoff * e->sp.mole_cutoff;
+    timer_begin(e, T_PAIRS);
+    CK(launch_centroids(e->crd, e->d_natoms, e->cen, n, e->S, e->st));
+    CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, nullptr, nullptr, 0, e->st));
+    std::vector<long long> cnt(n), off(n + 1, 0);
+    CK(cudaMemcpyAsync(cnt.data(), e->d_row_count, sizeof(long long) * n, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    for (int i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
+    const long long np = off[n];
+    if (np >= (1LL << 31)) return fail(EDMD_ERR_LIMIT, "%lld pairs exceeds the 2^31 pair-index limit", np);
+    if (int rc = ensure_pair_capacity(e, np)) return rc;
+    CK(cudaMemcpyAsync(e->d_row_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
+    CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, e->d_row_off, e->d_pairs, 1, e->st));
+    timer_end(e, T_PAIRS, 3);
+    std::vector<int2> pairs((size_t)np);
+    if (np) CK(cudaMemcpyAsync(pairs.data(), e->d_pairs, sizeof(int2) * np, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    e->np = np;
+    if (int rc = build_adjacency(e, pairs)) return rc;
+    e->have_pairs = true; e->hits_valid = false;
+    if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
+    if (num_pairs) *num_pairs = np;
+    return 0;
+}
+
+int edmd_get_pairlist(edmd_engine* e, int* pairs, long long cap_pairs) {
+    if (int rc = check_ready(e, true)) return rc;
+    if (!pairs || cap_pairs < e->np) return fail(EDMD_ERR_ARG, "pair buffer too small: %lld < %lld", cap_pairs, e->np);
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->st));
+    if (e->np) CK(cudaMemcpy(pairs, e->d_pairs, sizeof(int2) * e->np, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long np) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (np < 0 || (np > 0 && !pairs)) return fail(EDMD_ERR_ARG, "bad pair list");
+    if (np >= (1LL << 31)) return fail(EDMD_ERR_LIMIT, "%lld pairs exceeds the 2^31 pair-index limit", np);
+    CK(cudaSetDevice(e->device));
+    std::vector<int2> pv((size_t)np);
+    for (long long p = 0; p < np; p++) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        if (a < 0 || b < 0 || a >= e->n || b >= e->n || a == b)
+            return fail(EDMD_ERR_ARG, "pair %lld = (%d,%d) out of range", p, a, b);
+        pv[p] = make_int2(a, b);
+    }
+    CK(cudaStreamSynchronize(e->st));
+    if (int rc = ensure_pair_capacity(e, np)) return rc;
+    if (np) CK(cudaMemcpy(e->d_pairs, pv.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
+    e->np = np;
+    if (int rc = build_adjacency(e, pv)) return rc;
+    e->have_pairs = true; e->hits_valid = false;
+    if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
+    return 0;
+}
+
+int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (t0 < 0 || t1 > e->n || t0 > t1) return fail(EDMD_ERR_ARG, "tetrad shard [%d,%d) out of range", t0, t1);
+    if (p0 < 0 || p0 > p1 || (e->have_pairs && p1 > e->np)) return fail(EDMD_ERR_ARG, "pair shard out of range");
+    e->t0 = t0; e->t1 = t1; e->p0 = p0; e->p1 = p1; e->shard_pairs_custom = true;
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_ed_forces(edmd_engine* e) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    e->hits_valid = false;
+    return do_ed(e);
+}
+
+int edmd_random_terms(edmd_engine* e, int mode, long time0, int rank, long calls_before) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    return do_random(e, mode, time0, rank, calls_before);
+}
+
+int edmd_nb_scan(edmd_engine* e) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    return do_scan(e);
+}
+
+int edmd_nb_accumulate(edmd_engine* e) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    return do_accumulate(e, 1);
+}
+
+int edmd_nb_forces(edmd_engine* e) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    if (int rc = do_scan(e)) return rc;
+    return do_accumulate(e, 1);
+}
+
+int edmd_update_velocities(edmd_engine* e) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    return do_integrate(e, 1, 0);
+}
+
+int edmd_update_coordinates(edmd_engine* e) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    e->hits_valid = false;
+    return do_integrate(e, 0, 1);
+}
+
+int edmd_merge(edmd_engine* e) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!e->have_bp) return fail(EDMD_ERR_STATE, "edmd_merge needs bp_atoms (pass it to edmd_upload_tetrads)");
+    if (e->n < 4) return fail(EDMD_ERR_LIMIT, "merge needs at least 4 tetrads");
+    CK(cudaSetDevice(e->device));
+    timer_begin(e, T_MERGE);
+    CK(launch_merge(e->vel, e->crd, e->d_bp_off, e->n, e->S, e->st));
+    timer_end(e, T_MERGE, 1);
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_get_energies(edmd_engine* e, double out[4]) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    const int n = e->n;
+    std::vector<double> eed(n), enb(2 * (size_t)n), tmp(n);
+    CK(cudaMemcpyAsync(eed.data(), e->e_ed, sizeof(double) * n, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(enb.data(), e->e_nb, sizeof(double) * 2 * n, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaMemcpyAsync(tmp.data(), e->temp, sizeof(double) * n, cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    // master.cpp:393-401: sequential sums in tetrad order (4 doubles per tetrad; host side like
+    // the reference's master, output-frequency only)
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    for (int t = 0; t < n; t++) { out[0] += eed[t]; out[1] += enb[2 * (size_t)t]; out[2] += enb[2 * (size_t)t + 1]; out[3] += tmp[t]; }
+    out[3] /= n;
+    return 0;
+}
+
+int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->time0 = time0; e->rank = rank; e->calls = calls_before;
+    return 0;
+}
+
+int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    for (int it = 0; it < nsteps; it++) {
+        if (int rc = do_ed(e)) return rc;
+        if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls)) return rc;
+        if (random_mode == 1) e->calls += e->n;
+        if (int rc = do_scan(e)) return rc;
+        if (int rc = do_accumulate(e, 1)) return rc;
+        if (int rc = do_integrate(e, 1, 1)) return rc;
+    }
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_sync(edmd_engine* e) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes) {
+    if (int rc = check_ready(e, false)) return rc;
+    const size_t planes = sizeof(double) * (size_t)e->n * 3 * e->S;
+    void* p = nullptr; size_t b = 0;
+    switch (which) {
+        case EDMD_BUF_CRD: p = e->crd; b = planes; break;
+        case EDMD_BUF_VEL: p = e->vel; b = planes; break;
+        case EDMD_BUF_FED: p = e->fed; b = planes; break;
+        case EDMD_BUF_RND: p = e->rnd; b = planes; break;
+        case EDMD_BUF_FNB: p = e->fnb; b = planes; break;
+        case EDMD_BUF_HIT: p = e->d_hit; b = (size_t)e->np; break;
+        case EDMD_BUF_CENTROID: p = e->cen; b = sizeof(double) * 4 * (size_t)e->n; break;
+        default: return fail(EDMD_ERR_ARG, "unknown buffer %d", which);
+    }
+    if (dptr) *dptr = p;
+    if (bytes) *bytes = b;
+    return 0;
+}
+
+int edmd_atom_stride(edmd_engine* e) { return e ? e->S : 0; }
+int edmd_num_tetrads(edmd_engine* e) { return e ? e->n : 0; }
+long long edmd_num_pairs(edmd_engine* e) { return e ? e->np : 0; }
+void* edmd_stream(edmd_engine* e) { return e ? (void*)e->st : nullptr; }
+
+int edmd_timing_enable(edmd_engine* e, int on) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->timing = on != 0;
+    return 0;
+}
+int edmd_timing_get(edmd_engine* e, int which, double* total_ms, long long* launches) {
+    if (!e || which < 0 || which >= T_COUNT) return fail(EDMD_ERR_ARG, "bad timer id");
+    CK(cudaSetDevice(e->device));
+    timer_fold(e, which);
+    if (total_ms) *total_ms = e->timers[which].total_ms;
+    if (launches) *launches = e->timers[which].launches;
+    return 0;
+}
+int edmd_timing_reset(edmd_engine* e) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    for (int i = 0; i < T_COUNT; i++) { timer_fold(e, i); e->timers[i].total_ms = 0.0; e->timers[i].launches = 0; }
+    return 0;
+}
+long long edmd_launch_count(edmd_engine* e) { return e ? e->launches : 0; }
+
+int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    std::vector<unsigned char> h((size_t)e->np);
+    CK(cudaStreamSynchronize(e->st));
+    if (e->np) CK(cudaMemcpy(h.data(), e->d_hit, (size_t)e->np, cudaMemcpyDeviceToHost));
+    long long c = 0;
+    for (long long p = e->p0; p < e->p1; p++) c += h[p] != 0;
+    if (flagged_pairs) *flagged_pairs = c;
+    return 0;
+}
+
+int edmd_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return fail(EDMD_ERR_CUDA, "no CUDA device available");
+    CK(cudaSetDevice(device));
+    CK(measure_fp64_peak(tflops, sm_mhz_est));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,52 @@
+// kernels.h — host-callable launchers of the EDMD device kernels (one per .cu file).
+#pragma once
+#include <cuda_runtime.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace edmd {
+
+// Atom pairs with r^2 >= this cannot change any force or energy (see nb.cu header).
+inline double nb_effective_cut2(const SimParams& sp) {
+    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
+    if (sp.qfac == 0.0) return cut2 < 2.0 ? cut2 : 2.0;
+    return cut2;
+}
+
+cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, double* crd, double* fed,
+                             double* e_ed, int t0, int count, double scaled, cudaStream_t st);
+
+cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
+                           long long p0, long long p1, int S, double cut2_eff, int grid, cudaStream_t st);
+
+cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
+                                 const unsigned char* hit, const long long* adj_off, const int* adj_partner,
+                                 const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
+                                 const SimParams& sp, int use_hits, cudaStream_t st);
+
+cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
+                             const double* fed, const double* rnd, const double* fnb, double* temp,
+                             int t0, int count, int do_vel, int do_crd, const SimParams& sp,
+                             cudaStream_t st);
+
+cudaError_t launch_merge(double* vel, double* crd, const int* bp_off, int n, int S, cudaStream_t st);
+
+cudaError_t launch_centroids(const double* crd, const int* natoms, double* cen, int n, int S, cudaStream_t st);
+cudaError_t launch_pair_rows(const double* cen, int n, double cut2, double least, long long* row_count,
+                             const long long* row_off, int2* pairs, int fill, cudaStream_t st);
+
+// glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
+cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
+                                const SimParams& sp, long time0, int rank, long calls_before,
+                                cudaStream_t st);
+
+// interleaved xyz (reference layout, tetrads concatenated at off3[t]) <-> SoA planes
+cudaError_t launch_pack_planes(const double* flat, const long long* off3, const int* natoms, double* planes,
+                               int n, int S, cudaStream_t st);
+cudaError_t launch_unpack_planes(const double* planes, const long long* off3, const int* natoms, double* flat,
+                                 int n, int S, cudaStream_t st);
+
+// DFMA throughput microbenchmark (peak.cu)
+cudaError_t measure_fp64_peak(double* tflops, double* sm_mhz_est);
+
+}  // namespace edmd

@@ -1,0 +1,59 @@
+// peak.cu — FP64 roofline denominator: DFMA issue-rate microbenchmark.
+//
+// MEASURED_PEAKS.json carries HBM and bf16 figures only, so the NB kernel's FP64 roofline is
+// measured here: every thread runs 8 independent DFMA chains (no memory traffic), 148 x 8 CTAs
+// of 256 threads.  2 flops per DFMA.  Reported next to an SM-clock estimate from clock64().
+#include "common.cuh"
+#include "kernels.h"
+
+namespace edmd {
+
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, long long* cycles) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const long long t1 = clock64();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+
+cudaError_t measure_fp64_peak(double* tflops, double* sm_mhz_est) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = sms * 8, iters = 4096;
+    double* out = nullptr; long long* cyc = nullptr;
+    cudaError_t err = cudaMalloc(&out, sizeof(double) * grid * 256);
+    if (err != cudaSuccess) return err;
+    cudaMalloc(&cyc, sizeof(long long));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0, mhz = 0.0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        dfma_kernel<<<grid, 256>>>(out, iters, cyc);
+        cudaEventRecord(e1);
+        err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) break;
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * iters * 256.0 * grid;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        long long c = 0; cudaMemcpy(&c, cyc, sizeof(c), cudaMemcpyDeviceToHost);
+        if (rep > 0 && tf > best) { best = tf; mhz = (double)c / (ms * 1e-3) / 1e6; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out); cudaFree(cyc);
+    if (tflops) *tflops = best;
+    if (sm_mhz_est) *sm_mhz_est = mhz;
+    return err;
+}
+
+}  // namespace edmd

@@ -1,0 +1,129 @@
+// rng.cu — Langevin random terms with the reference's exact pseudo-random stream.
+//
+// Replaces EDMD::calculate_Random_Terms (/root/reference/src/edmd.cpp:170-228): per tetrad,
+// srand((unsigned)(RNG_Seed++ + rank^3 + time)) then 3*num_Atoms normal deviates from the
+// ACM-712 Kinderman-Monahan ratio-of-uniforms loop fed by libc rand(), each scaled by
+// sqrt(2*gamma*kT*m/dt).
+//
+// libc rand() is third-party (glibc TYPE_3 additive feedback generator, stdlib/random_r.c,
+// call sites edmd.cpp:179,206,207).  With Y the state rotated so that Y[l] = r[(l+3) % 31],
+// the generator is Y[m] = Y[m-31] + Y[m-3] (mod 2^32), output (Y[m] >> 1), and srand() discards
+// the first 310 outputs.  One warp owns one tetrad's stream: lane l holds element l of the
+// current 31-word block and the next block is N[l] = P[l] + N[l-3], i.e. a stride-3 inclusive
+// scan over lanes (four shuffles) plus P[28 + l%3] — no serial loop over the 2,070 uniforms.
+// Every Kinderman-Monahan trial consumes exactly two uniforms, accepted or not, so trial k of
+// the stream uses outputs 2k, 2k+1: 31 trials (two blocks) are tested in parallel and the
+// accepted ones are numbered with a ballot prefix count.  The result is the reference's
+// sequence, element for element.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace edmd {
+
+__device__ __forceinline__ unsigned lfg_next_block(unsigned P, int lane) {
+    // stride-3 inclusive scan of P over lanes 0..30
+    unsigned s = P;
+#pragma unroll
+    for (int d = 3; d < 31; d <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, s, d);
+        if (lane >= d) s += up;
+    }
+    const unsigned tail = __shfl_sync(0xffffffffu, P, 28 + lane % 3);
+    return s + tail;   // lane 31 carries garbage and is never read
+}
+
+struct RngArgs {
+    ParamSets ps;
+    const int* param_id;
+    double* rnd;         // [n][3][S]
+    int t0, count;
+    double gamma, scaled, dt;
+    long time0;
+    int rank;
+    long calls_before;   // calculate_Random_Terms calls made before tetrad t0 of this launch
+};
+
+__global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= A.count) return;
+    const int t = A.t0 + w;
+    const int ps = A.param_id[t];
+    const int S = A.ps.S;
+    const int n3 = 3 * A.ps.na[ps];
+    const double* M = A.ps.mass + (size_t)ps * 3 * S;
+    double* out = A.rnd + (size_t)t * 3 * S;
+
+    // seed: RNG_Seed starts at 13579, ++ per call, reset to 13579 once it exceeds 50,000,000
+    // (edmd.cpp:173,179-180): the value used by call number c (0-based) is 13579 + c % 49986422.
+    const long c = A.calls_before + w;
+    const unsigned rs = 13579u + (unsigned)(c % 49986422L);
+    unsigned seed = (unsigned)((long)(rs + (unsigned)(A.rank * A.rank * A.rank)) + A.time0);
+    if (seed == 0) seed = 1;
+
+    // srand(): r[0] = seed, r[i] = 16807 * r[i-1] mod 2147483647 (Schrage), i = 1..30
+    const int want = (lane + 3) % 31;   // lane l keeps r[(l+3) % 31]
+    int word = (int)seed;
+    unsigned P = (want == 0) ? seed : 0u;
+    for (int i = 1; i < 31; i++) {
+        const int hi = word / 127773, lo = word % 127773;
+        word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        if (i == want) P = (unsigned)word;
+    }
+    for (int b = 0; b < 10; b++) P = lfg_next_block(P, lane);   // 310 discarded outputs
+
+    int k = 0;   // normals produced so far (warp-uniform)
+    while (k < n3) {
+        const unsigned Ab = lfg_next_block(P, lane);
+        const unsigned Bb = lfg_next_block(Ab, lane);
+        P = Bb;
+        // trial `lane` (0..30) uses stream elements 2*lane, 2*lane+1 of the 62 just produced
+        const int e0 = 2 * lane, e1 = 2 * lane + 1;
+        const unsigned a0 = __shfl_sync(0xffffffffu, Ab, e0 < 31 ? e0 : 0);
+        const unsigned b0 = __shfl_sync(0xffffffffu, Bb, e0 >= 31 ? (e0 - 31) & 31 : 0);
+        const unsigned a1 = __shfl_sync(0xffffffffu, Ab, e1 < 31 ? e1 : 0);
+        const unsigned b1 = __shfl_sync(0xffffffffu, Bb, e1 >= 31 ? (e1 - 31) & 31 : 0);
+        const unsigned o0 = ((e0 < 31 ? a0 : b0) >> 1) & 0x7fffffffu;
+        const unsigned o1 = ((e1 < 31 ? a1 : b1) >> 1) & 0x7fffffffu;
+
+        bool accept = false;
+        double z = 0.0;
+        if (lane < 31) {   // edmd.cpp:206-216
+            const double u = (double)(int)o0 / 2147483647.0;
+            double v = (double)(int)o1 / 2147483647.0;
+            v = __dmul_rn(1.7156, __dsub_rn(v, 0.5));
+            const double x = __dsub_rn(u, 0.449871);
+            const double y = __dadd_rn(fabs(v), 0.386595);
+            const double q = __dadd_rn(__dmul_rn(x, x),
+                                       __dmul_rn(y, __dsub_rn(__dmul_rn(0.19600, y), __dmul_rn(0.25472, x))));
+            if (q < 0.27597) accept = true;
+            else if (!(q > 0.27846))
+                accept = __dmul_rn(v, v) < __dmul_rn(__dmul_rn(-4.0, log(u)), __dmul_rn(u, u));
+            z = v / u;
+        }
+        const unsigned acc = __ballot_sync(0xffffffffu, accept);
+        if (accept) {
+            const int idx = k + __popc(acc & ((1u << lane) - 1u));
+            if (idx < n3) {
+                const int a = idx / 3, cc = idx - 3 * a;
+                const double m = M[cc * S + a];
+                const double noise = sqrt(2.0 * A.gamma * A.scaled * m / A.dt);   // edmd.cpp:184
+                out[cc * S + a] = __dmul_rn(z, noise);                            // :223
+            }
+        }
+        k += __popc(acc);
+    }
+}
+
+cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
+                                const SimParams& sp, long time0, int rank, long calls_before,
+                                cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    RngArgs A{ps, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before};
+    const int wpb = 4;
+    random_terms_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace edmd
