@@ -131,6 +131,8 @@ int edmd_nb_accumulate(edmd_engine* e);
 /* EDMD::update_Velocities (edmd.cpp:289-317) and EDMD::update_Coordinates (:322-327). */
 int edmd_update_velocities(edmd_engine* e);
 int edmd_update_coordinates(edmd_engine* e);
+/* update_Velocity then update_Coordinate back to back (simulation.cpp:45-46) in one pass. */
+int edmd_integrate(edmd_engine* e);
 /* Master::merge_Vels_n_Crds (master.cpp:347-384). */
 int edmd_merge(edmd_engine* e);
 /* Master::write_Info sums (master.cpp:388-401): {sum E_ed, sum E_nb, sum E_el, mean T}. */
@@ -161,9 +163,13 @@ int edmd_atom_stride(edmd_engine* e);      /* S: atoms per tetrad plane, multipl
 int edmd_num_tetrads(edmd_engine* e);
 long long edmd_num_pairs(edmd_engine* e);
 void* edmd_stream(edmd_engine* e);         /* the cudaStream_t all engine work runs on    */
-/* Average device time (ms) per launch of each kernel since the last reset, measured with
- * CUDA events on the engine stream.  which: 0 ED, 1 NB scan, 2 NB accumulate+integrate,
- * 3 random, 4 merge, 5 pair list. */
+/* Device time of everything enqueued between the two calls, CUDA events on the engine
+ * stream (torch.cuda.Event would only see torch's current stream).  stop synchronises. */
+int edmd_timer_start(edmd_engine* e);
+int edmd_timer_stop(edmd_engine* e, double* ms);
+/* Accumulated device time (ms) and launch count per kernel since the last reset, measured
+ * with CUDA events on the engine stream.  which: 0 ED, 1 NB scan, 2 NB accumulate+clip,
+ * 3 random, 4 merge, 5 pair list, 6 integrate, 7 layout (pack/unpack at the boundary). */
 int edmd_timing_enable(edmd_engine* e, int on);
 int edmd_timing_get(edmd_engine* e, int which, double* total_ms, long long* launches);
 int edmd_timing_reset(edmd_engine* e);

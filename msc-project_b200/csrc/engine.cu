@@ -106,6 +106,7 @@ struct edmd_engine {
     long calls = 0;
 
     int scan_grid = 592;
+    cudaEvent_t span0 = nullptr, span1 = nullptr;   // edmd_timer_start/stop
     bool timing = false;
     Timer timers[T_COUNT];
     long long launches = 0;
@@ -330,6 +331,7 @@ void edmd_destroy(edmd_engine* e) {
     cudaSetDevice(e->device);
     for (int i = 0; i < T_COUNT; i++) timer_fold(e, i);
     free_system(e);
+    if (e->span0) { cudaEventDestroy(e->span0); cudaEventDestroy(e->span1); }
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -695,6 +697,13 @@ int edmd_update_coordinates(edmd_engine* e) {
     return do_integrate(e, 0, 1);
 }
 
+int edmd_integrate(edmd_engine* e) {
+    if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    e->hits_valid = false;
+    return do_integrate(e, 1, 1);
+}
+
 int edmd_merge(edmd_engine* e) {
     if (int rc = check_ready(e, false)) return rc;
     if (!e->have_bp) return fail(EDMD_ERR_STATE, "edmd_merge needs bp_atoms (pass it to edmd_upload_tetrads)");
@@ -775,6 +784,24 @@ int edmd_atom_stride(edmd_engine* e) { return e ? e->S : 0; }
 int edmd_num_tetrads(edmd_engine* e) { return e ? e->n : 0; }
 long long edmd_num_pairs(edmd_engine* e) { return e ? e->np : 0; }
 void* edmd_stream(edmd_engine* e) { return e ? (void*)e->st : nullptr; }
+
+int edmd_timer_start(edmd_engine* e) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    if (!e->span0) { CK(cudaEventCreate(&e->span0)); CK(cudaEventCreate(&e->span1)); }
+    CK(cudaEventRecord(e->span0, e->st));
+    return 0;
+}
+int edmd_timer_stop(edmd_engine* e, double* ms) {
+    if (!e || !e->span0) return fail(EDMD_ERR_STATE, "edmd_timer_stop without edmd_timer_start");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventRecord(e->span1, e->st));
+    CK(cudaEventSynchronize(e->span1));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, e->span0, e->span1));
+    if (ms) *ms = f;
+    return 0;
+}
 
 int edmd_timing_enable(edmd_engine* e, int on) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, long 
     }
     const long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+    if ((threadIdx.x & 31) == 0) atomicMax((unsigned long long*)cycles, (unsigned long long)(t1 - t0));
 }
 
 cudaError_t measure_fp64_peak(double* tflops, double* sm_mhz_est) {
@@ -38,6 +38,7 @@ cudaError_t measure_fp64_peak(double* tflops, double* sm_mhz_est) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     double best = 0.0, mhz = 0.0;
     for (int rep = 0; rep < 6; rep++) {
+        cudaMemset(cyc, 0, sizeof(long long));
         cudaEventRecord(e0);
         dfma_kernel<<<grid, 256>>>(out, iters, cyc);
         cudaEventRecord(e1);

@@ -1,0 +1,206 @@
+"""Multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
+
+Replaces the reference's MPI master/worker decomposition
+(/root/reference/src/master.cpp:214-292 generate_Indexes / send_Workload_Indexes /
+calculate_Forces, src/worker.cpp:109-187, src/mpilib.cpp): there is no master.  Every rank
+holds the whole system on its GPU (as every MPI worker did, worker.cpp:67-87) but computes
+only its shard:
+
+  * tetrads are split into contiguous equal blocks (owner of a tetrad runs its ED force, random
+    term, NB accumulation + clip, velocity and coordinate update);
+  * the flat tetrad-pair list is split into contiguous equal slices for the FP64 distance pass
+    (the reference's NB_Index split, master.cpp:225-239).
+
+Per step the path has two real exchange points, both all-gathers over NCCL/NVLink issued on
+the engine's own CUDA stream:
+    ED (owned) -> all-gather post-shake coordinates (replaces MPI_Bcast(MPI_Crds), master.cpp:279)
+    NB scan (own pair slice) -> all-gather per-pair hit flags (replaces the dense
+        MPI_Reduce of N x 758 doubles, master.cpp:288: one byte per pair instead)
+    NB accumulate + clip + integrate (owned), deterministic: each tetrad is summed by one CTA.
+No force reduction is needed, so results are bit-identical for every world size.
+
+``ShardPlan`` is pure host logic (tested on CPU with gloo, world_size 2).  ``ShardedEngine``
+works with any backend object exposing the small method set of ``EngineBackend`` below.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def block_range(total: int, world: int, rank: int):
+    """Equal contiguous blocks of ceil(total/world); the tail block may be short or empty."""
+    chunk = -(-total // world) if total > 0 else 0
+    lo = min(total, rank * chunk)
+    hi = min(total, lo + chunk)
+    return lo, hi, chunk
+
+
+class ShardPlan:
+    def __init__(self, n_tetrads: int, n_pairs: int, world: int, rank: int):
+        self.n, self.np, self.world, self.rank = n_tetrads, n_pairs, world, rank
+        self.t0, self.t1, self.t_chunk = block_range(n_tetrads, world, rank)
+        self.p0, self.p1, self.p_chunk = block_range(n_pairs, world, rank)
+
+    def tetrad_range(self, r):
+        return block_range(self.n, self.world, r)[:2]
+
+    def pair_range(self, r):
+        return block_range(self.np, self.world, r)[:2]
+
+    @property
+    def even_tetrads(self):
+        return self.n == self.t_chunk * self.world
+
+    @property
+    def even_pairs(self):
+        return self.np == self.p_chunk * self.world
+
+
+class _CudaView:
+    """__cuda_array_interface__ shim so torch can wrap an engine-owned device buffer."""
+
+    def __init__(self, ptr, nbytes, typestr, itemsize):
+        self.__cuda_array_interface__ = {"shape": (nbytes // itemsize,), "typestr": typestr,
+                                         "data": (ptr, False), "version": 2}
+
+
+class EngineBackend:
+    """Adapter: msc-project_b200 Engine + torch CUDA tensors over its buffers."""
+
+    def __init__(self, engine, device):
+        import torch
+        self.torch = torch
+        self.e = engine
+        self.device = device
+        self.stream = torch.cuda.ExternalStream(engine.stream, device=device)
+        self.S = engine.atom_stride
+        self._crd = None
+        self._vel = None
+        self._hit = None
+
+    def _wrap(self, which, typestr, itemsize, dtype):
+        ptr, nbytes = self.e.device_buffer(which)
+        return self.torch.as_tensor(_CudaView(ptr, nbytes, typestr, itemsize), device=self.device).view(dtype)
+
+    def crd_tensor(self):
+        if self._crd is None:
+            self._crd = self._wrap(self.e.BUF_CRD, "<f8", 8, self.torch.float64)
+        return self._crd
+
+    def vel_tensor(self):
+        if self._vel is None:
+            self._vel = self._wrap(self.e.BUF_VEL, "<f8", 8, self.torch.float64)
+        return self._vel
+
+    def hit_tensor(self):
+        ptr, nbytes = self.e.device_buffer(self.e.BUF_HIT)
+        if self._hit is None or self._hit[0] != (ptr, nbytes):
+            self._hit = ((ptr, nbytes), self._wrap(self.e.BUF_HIT, "|u1", 1, self.torch.uint8))
+        return self._hit[1]
+
+    def invalidate(self):
+        self._hit = None
+
+    @property
+    def plane_elems(self):   # doubles per tetrad in a state buffer
+        return 3 * self.S
+
+    def stream_ctx(self):
+        return self.torch.cuda.stream(self.stream)
+
+    # compute
+    def set_shard(self, t0, t1, p0, p1): self.e.set_shard(t0, t1, p0, p1)
+    def ed_forces(self): self.e.ed_forces()
+    def random_terms(self, mode, time0, rank, calls): self.e.random_terms(mode, time0, rank, calls)
+    def nb_scan(self): self.e.nb_scan()
+    def nb_accumulate(self): self.e.nb_accumulate()
+    def integrate(self): self.e.integrate()
+    def merge(self): self.e.merge()
+    def build_pairlist(self): return self.e.build_pairlist()
+    def sync(self): self.e.sync()
+
+
+class ShardedEngine:
+    """Runs the reference step protocol (simulation.cpp:34-55) over world_size ranks."""
+
+    def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None):
+        self.b, self.dist, self.n, self.rank, self.world, self.group = backend, dist, n_tetrads, rank, world, group
+        self.plan = None
+        self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
+
+    # -- collectives -------------------------------------------------------------------
+    def _all_gather_blocks(self, flat, elems_per_unit, total_units, chunk_units):
+        """In-place all-gather of contiguous per-rank blocks of `flat` (a 1-D tensor)."""
+        if self.world == 1:
+            return
+        even = total_units == chunk_units * self.world
+        lo, hi, _ = block_range(total_units, self.world, self.rank)
+        if even:
+            mine = flat[lo * elems_per_unit: hi * elems_per_unit]
+            self.dist.all_gather_into_tensor(flat[: total_units * elems_per_unit], mine, group=self.group)
+        else:
+            parts = []
+            for r in range(self.world):
+                a, b, _ = block_range(total_units, self.world, r)
+                parts.append(flat[a * elems_per_unit: b * elems_per_unit])
+            # uneven blocks: one broadcast per non-empty block
+            for r, part in enumerate(parts):
+                if part.numel():
+                    self.dist.broadcast(part, src=r if self.group is None else self.dist.get_global_rank(self.group, r),
+                                        group=self.group)
+
+    def gather_coordinates(self):
+        self._all_gather_blocks(self.b.crd_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
+
+    def gather_velocities(self):
+        self._all_gather_blocks(self.b.vel_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
+
+    def gather_hits(self):
+        self._all_gather_blocks(self.b.hit_tensor(), 1, self.plan.np, self.plan.p_chunk)
+
+    @property
+    def plan_t_chunk(self):
+        return block_range(self.n, self.world, 0)[2]
+
+    # -- protocol ----------------------------------------------------------------------
+    def build_pairlist(self) -> int:
+        """Every rank builds the same list from the same (gathered) coordinates — the list is
+        a pure function of the centroids, so no exchange is needed (master.cpp:180-210)."""
+        t0, t1, _ = block_range(self.n, self.world, self.rank)
+        self.b.set_shard(0, self.n, 0, 0)
+        npairs = self.b.build_pairlist()
+        self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
+        self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)
+        if hasattr(self.b, "invalidate"):
+            self.b.invalidate()
+        return npairs
+
+    def set_rng(self, time0, rank, calls):
+        self.time0, self.rng_rank, self.calls = time0, rank, calls
+
+    def step(self, nsteps=1, random_mode=0):
+        with self.b.stream_ctx():
+            for _ in range(nsteps):
+                self.b.ed_forces()
+                self.b.random_terms(random_mode, self.time0, self.rng_rank, self.calls)
+                if random_mode == 1:
+                    self.calls += self.n
+                self.gather_coordinates()
+                self.b.nb_scan()
+                self.gather_hits()
+                self.b.nb_accumulate()
+                self.b.integrate()
+
+    def merge(self):
+        """4-fold overlap average needs neighbours' copies: gather state, merge everywhere."""
+        with self.b.stream_ctx():
+            self.gather_coordinates()
+            self.gather_velocities()
+            self.b.merge()
+
+    def finish(self):
+        """Make every rank's copy of coordinates and velocities complete (for output)."""
+        with self.b.stream_ctx():
+            self.gather_coordinates()
+            self.gather_velocities()
+        self.b.sync()

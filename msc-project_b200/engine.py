@@ -89,6 +89,7 @@ def load_library():
         "edmd_nb_accumulate": (C.c_int, [E]),
         "edmd_update_velocities": (C.c_int, [E]),
         "edmd_update_coordinates": (C.c_int, [E]),
+        "edmd_integrate": (C.c_int, [E]),
         "edmd_merge": (C.c_int, [E]),
         "edmd_get_energies": (C.c_int, [E, PD]),
         "edmd_set_rng": (C.c_int, [E, C.c_long, C.c_int, C.c_long]),
@@ -99,6 +100,8 @@ def load_library():
         "edmd_num_tetrads": (C.c_int, [E]),
         "edmd_num_pairs": (LL, [E]),
         "edmd_stream": (C.c_void_p, [E]),
+        "edmd_timer_start": (C.c_int, [E]),
+        "edmd_timer_stop": (C.c_int, [E, PD]),
         "edmd_timing_enable": (C.c_int, [E, C.c_int]),
         "edmd_timing_get": (C.c_int, [E, C.c_int, PD, C.POINTER(LL)]),
         "edmd_timing_reset": (C.c_int, [E]),
@@ -309,6 +312,9 @@ class Engine:
     def update_coordinates(self):
         self._ck(self.lib.edmd_update_coordinates(self.h))
 
+    def integrate(self):
+        self._ck(self.lib.edmd_integrate(self.h))
+
     def merge(self):
         self._ck(self.lib.edmd_merge(self.h))
 
@@ -339,6 +345,14 @@ class Engine:
     @property
     def atom_stride(self):
         return self.lib.edmd_atom_stride(self.h)
+
+    def timer_start(self):
+        self._ck(self.lib.edmd_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.edmd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def timing(self, on=True):
         self._ck(self.lib.edmd_timing_enable(self.h, int(on)))
