@@ -3,13 +3,27 @@
 // Replaces EDMD::calculate_ED_Forces (/root/reference/src/edmd.cpp:64-166) and the QCP
 // routines it calls (src/qcprot/qcprot.c:90-407), batched over tetrads.
 //
-// One CTA of 256 threads per tetrad, thread a <-> atom a.  Each thread keeps its atom's
-// 3 x nev eigenvector coefficients in registers between the projection pass and the
-// re-embedding pass, so the 72.6 KB eigenvector block crosses the memory system once
-// (the reference walks it twice, the second time with stride 3N, edmd.cpp:106-127).
-// Reductions (centroids, 3x3 cross-covariance, projections) are fixed-order CTA sums.
-// Roofline: HBM — 96,872 algorithmic bytes per tetrad (SURVEY.md §8a a-ED); with
-// de-duplicated parameter sets resident in L2 the DRAM traffic drops to the 24 KB of state.
+// Two kernels per batch:
+//
+//  superpose_kernel (64 threads per tetrad, up to 10 tetrads resident per SM): centroids, 3x3
+//    cross-covariance, QCP rotation and the offset vector.  The rotation feeds
+//    d = R*x_c - avg_c, a difference of ~10 A vectors that is ~0.1 A long, so last-bit
+//    differences of the sums are amplified ~100x into the forces.  To stay robustly inside the
+//    1e-10 parity bound (and usually at 1e-15) the 20 reductions are done in the reference's
+//    SEQUENTIAL atom order (qcprot.c:370-379, 132-157; edmd.cpp:97-101): per-atom terms are
+//    produced in parallel into shared memory, then lane k of one warp runs the k-th running sum
+//    as a chain of 252 DADDs.  This file is compiled with -fmad=false, so every expression
+//    rounds exactly like the CPU build and R, centroids and offset are BIT-IDENTICAL to the
+//    reference's.  Latency-bound (3 x 252 dependent adds) and hidden by occupancy.
+//
+//  ed_project_kernel (256 threads per tetrad, thread a <-> atom a): displacement, projections
+//    on the eigenvectors (fixed-order CTA tree sums — the only place the summation order differs
+//    from the CPU, ~1e-16 relative), re-embedding, force, rotation back.  Each thread keeps its
+//    atom's 3 x nev eigenvector coefficients in registers between the projection pass and the
+//    re-embedding pass, so the 72.6 KB eigenvector block crosses the memory system once (the
+//    reference walks it twice, the second time with stride 3N, edmd.cpp:106-127).
+//    Roofline: HBM — 96,872 algorithmic bytes per tetrad (SURVEY.md §8a a-ED); with
+//    de-duplicated parameter sets resident in L2 the DRAM traffic drops to the 24 KB of state.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -101,19 +115,126 @@ __device__ void qcp_rotation(double R[9], const double M[9], double e0) {
     R[6] = 2 * (ki + wj);     R[7] = 2 * (jk - wi);     R[8] = w2 - i2 - j2 + k2;
 }
 
+constexpr int kSupThreads = 64;
+constexpr int kSupWords = 24;   // per tetrad: R[9], shift[3], avg centroid[3], x centroid[3], pad
+
+struct SupArgs {
+    ParamSets ps;
+    const int* param_id;
+    const double* crd;   // [n][3][S]
+    double* sup;         // [n][kSupWords] out
+    int t0;
+};
+
+// lane k < nsum: running sum of buf[k][0..na) in atom order, starting from 0.0
+// rows are padded by one double so that lanes k = 0..10 hit distinct shared-memory banks
+constexpr int kSupRow = kMaxStride + 1;
+__device__ __forceinline__ double seq_sum(const double (*buf)[kSupRow], int k, int nsum, int na) {
+    double s = 0.0;
+    if (k < nsum) {
+        const double* row = buf[k];
+#pragma unroll 4
+        for (int i = 0; i < na; i++) s = s + row[i];
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kSupThreads) superpose_kernel(SupArgs A) {
+    __shared__ double buf[11][kSupRow];
+    __shared__ double sC[6];
+    __shared__ double sR[9];
+    const int t = A.t0 + blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ps = A.param_id[t];
+    const int na = A.ps.na[ps];
+    const int S = A.ps.S;
+    const double* X = A.crd + (size_t)t * 3 * S;
+    const double* AV = A.ps.avg + (size_t)ps * 3 * S;
+    constexpr int R4 = kMaxStride / kSupThreads;   // atoms per thread
+
+    double x[R4][3], a[R4][3];
+#pragma unroll
+    for (int r = 0; r < R4; r++) {
+        const int i = tid + kSupThreads * r;
+        if (i < na) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                a[r][c] = AV[c * S + i]; x[r][c] = X[c * S + i];
+                buf[c][i] = a[r][c]; buf[3 + c][i] = x[r][c];
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {   // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
+        const double s = seq_sum(buf, lane, 6, na);
+        if (lane < 6) sC[lane] = s / na;
+    }
+    __syncthreads();
+    double ca[3], cx[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { ca[c] = sC[c]; cx[c] = sC[3 + c]; }
+#pragma unroll
+    for (int r = 0; r < R4; r++) {   // InnerProduct terms, qcprot.c:134-156
+        const int i = tid + kSupThreads * r;
+        if (i < na) {
+            const double a0 = a[r][0] - ca[0], a1 = a[r][1] - ca[1], a2 = a[r][2] - ca[2];
+            const double x0 = x[r][0] - cx[0], x1 = x[r][1] - cx[1], x2 = x[r][2] - cx[2];
+            buf[0][i] = (a0 * x0); buf[1][i] = (a0 * x1); buf[2][i] = (a0 * x2);
+            buf[3][i] = (a1 * x0); buf[4][i] = (a1 * x1); buf[5][i] = (a1 * x2);
+            buf[6][i] = (a2 * x0); buf[7][i] = (a2 * x1); buf[8][i] = (a2 * x2);
+            buf[9][i] = a0 * a0 + a1 * a1 + a2 * a2;
+            buf[10][i] = (x0 * x0 + x1 * x1 + x2 * x2);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const double s = seq_sum(buf, lane, 11, na);
+        double m[11];
+#pragma unroll
+        for (int k = 0; k < 11; k++) m[k] = __shfl_sync(0xffffffffu, s, k);
+        double R[9];
+        qcp_rotation(R, m, (m[9] + m[10]) * 0.5);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) sR[k] = R[k];
+        }
+    }
+    __syncthreads();
+    double R[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = sR[k];
+#pragma unroll
+    for (int r = 0; r < R4; r++) {   // offset-vector terms on the UNCENTRED arrays, edmd.cpp:97-101
+        const int i = tid + kSupThreads * r;
+        if (i < na) {
+            buf[0][i] = (a[r][0] - (R[0] * x[r][0] + R[1] * x[r][1] + R[2] * x[r][2]));
+            buf[1][i] = (a[r][1] - (R[3] * x[r][0] + R[4] * x[r][1] + R[5] * x[r][2]));
+            buf[2][i] = (a[r][2] - (R[6] * x[r][0] + R[7] * x[r][1] + R[8] * x[r][2]));
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const double s = seq_sum(buf, lane, 3, na);
+        double* out = A.sup + (size_t)t * kSupWords;
+        if (lane < 3) out[9 + lane] = s / na;          // edmd.cpp:102
+        if (lane < 9) out[lane] = R[lane];
+        if (lane < 6) out[12 + lane] = sC[lane];
+    }
+}
+
 struct EdArgs {
     ParamSets ps;
     const int* param_id;
-    double* crd;        // [n][3][S] in/out (overwritten with the re-embedded coordinates)
-    double* fed;        // [n][3][S] out
-    double* e_ed;       // [n] out
-    int t0;             // first tetrad of this launch
+    double* crd;         // [n][3][S] in/out (overwritten with the re-embedded coordinates)
+    double* fed;         // [n][3][S] out
+    double* e_ed;        // [n] out
+    const double* sup;   // [n][kSupWords] from superpose_kernel
+    int t0;              // first tetrad of this launch
     double scaled;
 };
 
-__global__ void __launch_bounds__(kThreads, 2) ed_forces_kernel(EdArgs A) {
+__global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
     __shared__ double red[16][kWarps];
-    __shared__ double sR[9];
     __shared__ double sProj[64];
     __shared__ double sPw[64];
 
@@ -127,13 +248,13 @@ __global__ void __launch_bounds__(kThreads, 2) ed_forces_kernel(EdArgs A) {
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
     const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
     const double* EL = A.ps.eval + (size_t)ps * A.ps.NEV;
+    const double* SUP = A.sup + (size_t)t * kSupWords;
 
     double x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0;
     if (on) {
         x0 = X[tid]; x1 = X[S + tid]; x2 = X[2 * S + tid];
         a0 = AV[tid]; a1 = AV[S + tid]; a2 = AV[2 * S + tid];
     }
-    // first eigenvector chunk: issue the loads early, they are independent of the QCP
     double ev[kNevReg][3];
     const int nchunk0 = nev < kNevReg ? nev : kNevReg;
 #pragma unroll
@@ -144,47 +265,23 @@ __global__ void __launch_bounds__(kThreads, 2) ed_forces_kernel(EdArgs A) {
             ev[j][0] = e[tid]; ev[j][1] = e[S + tid]; ev[j][2] = e[2 * S + tid];
         }
     }
-
-    // centroids — CenterCoords, qcprot.c:370-387
-    double c[6] = {a0, a1, a2, x0, x1, x2};
-    block_sum<6>(c, red);
-    double ac0 = 0, ac1 = 0, ac2 = 0, xc0 = 0, xc1 = 0, xc2 = 0;
-    if (on) {
-        ac0 = a0 - c[0] / na; ac1 = a1 - c[1] / na; ac2 = a2 - c[2] / na;
-        xc0 = x0 - c[3] / na; xc1 = x1 - c[4] / na; xc2 = x2 - c[5] / na;
-    }
-    // cross-covariance + inner products — InnerProduct, qcprot.c:132-160
-    double m[11] = {ac0 * xc0, ac0 * xc1, ac0 * xc2, ac1 * xc0, ac1 * xc1, ac1 * xc2,
-                    ac2 * xc0, ac2 * xc1, ac2 * xc2,
-                    ac0 * ac0 + ac1 * ac1 + ac2 * ac2, xc0 * xc0 + xc1 * xc1 + xc2 * xc2};
-    block_sum<11>(m, red);
-    if (tid < 32) {   // one warp solves the quartic; the other seven wait at the barrier
-        double R[9];
-        qcp_rotation(R, m, (m[9] + m[10]) * 0.5);
-        if (tid == 0) {
-#pragma unroll
-            for (int k = 0; k < 9; k++) sR[k] = R[k];
-        }
-    }
-    __syncthreads();
     double R[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = sR[k];
+    for (int k = 0; k < 9; k++) R[k] = SUP[k];
+    const double shift0 = SUP[9], shift1 = SUP[10], shift2 = SUP[11];
 
-    // displacement in the reference frame (edmd.cpp:89-94) and offset vector (:97-102)
-    double d0 = 0, d1 = 0, d2 = 0, h0 = 0, h1 = 0, h2 = 0;
+    // displacement in the reference frame, edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
+    double d0 = 0, d1 = 0, d2 = 0;
     if (on) {
+        const double ac0 = a0 - SUP[12], ac1 = a1 - SUP[13], ac2 = a2 - SUP[14];
+        const double xc0 = x0 - SUP[15], xc1 = x1 - SUP[16], xc2 = x2 - SUP[17];
         d0 = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
         d1 = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
         d2 = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
-        h0 = a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2);
-        h1 = a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2);
-        h2 = a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2);
     }
 
     // projections (edmd.cpp:106-110), kNevReg eigenvectors per pass
-    double shift0 = 0, shift1 = 0, shift2 = 0;
-    for (int j0 = 0; j0 < nev || j0 == 0; j0 += kNevReg) {
+    for (int j0 = 0; j0 < nev; j0 += kNevReg) {
         if (j0 > 0) {
 #pragma unroll
             for (int j = 0; j < kNevReg; j++) {
@@ -195,12 +292,10 @@ __global__ void __launch_bounds__(kThreads, 2) ed_forces_kernel(EdArgs A) {
                 }
             }
         }
-        double v[kNevReg + 3];
+        double v[kNevReg];
 #pragma unroll
         for (int j = 0; j < kNevReg; j++) v[j] = ev[j][0] * d0 + ev[j][1] * d1 + ev[j][2] * d2;
-        v[kNevReg] = h0; v[kNevReg + 1] = h1; v[kNevReg + 2] = h2;
-        block_sum<kNevReg + 3>(v, red);
-        if (j0 == 0) { shift0 = v[kNevReg] / na; shift1 = v[kNevReg + 1] / na; shift2 = v[kNevReg + 2] / na; }
+        block_sum<kNevReg>(v, red);
         if (tid < kNevReg && j0 + tid < nev) {
             sProj[j0 + tid] = v[tid];
             sPw[j0 + tid] = v[tid] * A.scaled / EL[j0 + tid];
@@ -249,10 +344,14 @@ __global__ void __launch_bounds__(kThreads, 2) ed_forces_kernel(EdArgs A) {
 }
 
 cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, double* crd, double* fed,
-                             double* e_ed, int t0, int count, double scaled, cudaStream_t st) {
+                             double* e_ed, double* sup, int t0, int count, double scaled, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    EdArgs A{ps, param_id, crd, fed, e_ed, t0, scaled};
-    ed_forces_kernel<<<count, kThreads, 0, st>>>(A);
+    SupArgs B{ps, param_id, crd, sup, t0};
+    superpose_kernel<<<count, kSupThreads, 0, st>>>(B);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return err;
+    EdArgs A{ps, param_id, crd, fed, e_ed, sup, t0, scaled};
+    ed_project_kernel<<<count, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }
 

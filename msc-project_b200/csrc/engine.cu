@@ -74,7 +74,7 @@ struct edmd_engine {
 
     // device: state planes
     double *crd = nullptr, *vel = nullptr, *fed = nullptr, *rnd = nullptr, *fnb = nullptr;
-    double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr;
+    double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     bool rnd_zero = true;   // random terms currently all zero
 
     // staging (interleaved flat), 3 slots
@@ -146,13 +146,13 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
     cudaFree(e->d_eval); cudaFree(e->d_evec);
     cudaFree(e->crd); cudaFree(e->vel); cudaFree(e->fed); cudaFree(e->rnd); cudaFree(e->fnb);
-    cudaFree(e->e_ed); cudaFree(e->e_nb); cudaFree(e->temp); cudaFree(e->cen);
+    cudaFree(e->e_ed); cudaFree(e->e_nb); cudaFree(e->temp); cudaFree(e->cen); cudaFree(e->sup);
     cudaFree(e->d_stage); if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_row_count); cudaFree(e->d_row_off);
     cudaFree(e->d_adj_off); cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair); cudaFree(e->d_bp_off);
     e->d_natoms = e->d_param_id = e->d_ps_na = e->d_ps_nev = nullptr; e->d_off3 = nullptr;
     e->d_avg = e->d_mass = e->d_chg = e->d_eval = e->d_evec = nullptr;
-    e->crd = e->vel = e->fed = e->rnd = e->fnb = e->e_ed = e->e_nb = e->temp = e->cen = nullptr;
+    e->crd = e->vel = e->fed = e->rnd = e->fnb = e->e_ed = e->e_nb = e->temp = e->cen = e->sup = nullptr;
     e->d_stage = nullptr; e->h_stage = nullptr;
     e->d_pairs = nullptr; e->d_hit = nullptr; e->d_row_count = e->d_row_off = e->d_adj_off = nullptr;
     e->d_adj_partner = e->d_adj_pair = nullptr; e->d_bp_off = nullptr;
@@ -231,8 +231,8 @@ int check_ready(edmd_engine* e, bool need_pairs) {
 
 int do_ed(edmd_engine* e) {
     timer_begin(e, T_ED);
-    CK(launch_ed_forces(e->ps, e->d_param_id, e->crd, e->fed, e->e_ed, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
-    timer_end(e, T_ED, 1);
+    CK(launch_ed_forces(e->ps, e->d_param_id, e->crd, e->fed, e->e_ed, e->sup, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
+    timer_end(e, T_ED, 2);
     return 0;
 }
 int do_scan(edmd_engine* e) {
@@ -435,6 +435,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
+    CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
     CK(dev_alloc(&e->d_stage, 3 * (size_t)e->total3));
     CK(cudaMallocHost((void**)&e->h_stage, sizeof(double) * 3 * (size_t)e->total3));
     CK(dev_alloc(&e->d_row_count, n)); CK(dev_alloc(&e->d_row_off, n + 1)); CK(dev_alloc(&e->d_adj_off, n + 1));

@@ -1,0 +1,160 @@
+"""World-size-2 test of the multi-GPU step protocol on CPU (gloo): the sharding plan, the two
+all-gathers and the owner-computes accumulation of msc-project_b200/dist.py, with the compute
+done by the CPU oracle standing in for the engine.  Result must equal the single-rank oracle
+bit for bit (no force reduction exists in the protocol, so there is no reordering)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class OracleBackend:
+    """Implements the backend surface of dist.ShardedEngine on top of the CPU oracle."""
+
+    def __init__(self, po, system):
+        self.po, self.sys = po, system
+        self.o = po.Oracle(system, "port")
+        self.n = system.n
+        self.off = system.off3
+        self.S = 252
+        self.crd = torch.zeros(self.n * 3 * self.S, dtype=torch.float64)
+        self.vel = torch.zeros(self.n * 3 * self.S, dtype=torch.float64)
+        self.hit = torch.zeros(0, dtype=torch.uint8)
+        self.t0, self.t1, self.p0, self.p1 = 0, self.n, 0, 0
+        self.fnb = np.zeros(system.crd.size)
+        self._push()
+
+    # the dist layer sees one flat tensor with tetrad-major blocks; layout inside a block is free
+    def _push(self):
+        c, v = self.o.get_state()
+        self.crd.view(self.n, -1)[:, :756] = torch.from_numpy(c.reshape(self.n, 756))
+        self.vel.view(self.n, -1)[:, :756] = torch.from_numpy(v.reshape(self.n, 756))
+
+    def _pull(self):
+        c = self.crd.view(self.n, -1)[:, :756].numpy().reshape(-1).copy()
+        v = self.vel.view(self.n, -1)[:, :756].numpy().reshape(-1).copy()
+        self.o.set_state(c, v)
+
+    plane_elems = 3 * 252
+
+    def crd_tensor(self): return self.crd
+    def vel_tensor(self): return self.vel
+    def hit_tensor(self): return self.hit
+
+    def stream_ctx(self):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def set_shard(self, t0, t1, p0, p1): self.t0, self.t1, self.p0, self.p1 = t0, t1, p0, p1
+
+    def build_pairlist(self):
+        self._pull()
+        npairs = self.o.build_pairs()
+        self.pairs = self.o.get_pairs()
+        self.hit = torch.zeros(npairs, dtype=torch.uint8)
+        return npairs
+
+    def ed_forces(self):
+        self._pull()
+        for t in range(self.t0, self.t1):
+            self.o.ed_forces(t)
+        self._push()
+
+    def random_terms(self, mode, time0, rank, calls):
+        assert mode == 0
+
+    def nb_scan(self):
+        self._pull()
+        for p in range(self.p0, self.p1):
+            t1, t2 = map(int, self.pairs[p])
+            self.o.nb_forces_pair(t1, t2)
+            f = self.o.get_forces()
+            any_hit = np.any(f["nb"][self.off[t1]:self.off[t1 + 1]] != 0) or f["nb_energy"][t1].any()
+            self.hit[p] = 1 if any_hit else 0
+
+    def nb_accumulate(self):
+        acc = np.zeros(self.sys.crd.size)
+        for p, (t1, t2) in enumerate(self.pairs):
+            if not self.hit[p]:
+                continue
+            own1, own2 = self.t0 <= t1 < self.t1, self.t0 <= t2 < self.t1
+            if not (own1 or own2):
+                continue
+            self.o.nb_forces_pair(int(t1), int(t2))
+            f = self.o.get_forces()["nb"]
+            for t, own in ((t1, own1), (t2, own2)):
+                if own:
+                    acc[self.off[t]:self.off[t + 1]] += f[self.off[t]:self.off[t + 1]]
+        self.fnb = np.clip(acc, -1.0, 1.0)
+
+    def integrate(self):
+        f = self.o.get_forces()
+        self.o.set_forces(None, np.zeros_like(self.fnb), self.fnb)
+        for t in range(self.t0, self.t1):
+            self.o.update_velocities(t); self.o.update_coordinates(t)
+        self._push()
+
+    def merge(self):
+        self._pull(); self.o.merge(); self._push()
+
+    def sync(self): pass
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    pkg = importlib.import_module("msc-project_b200")
+    dmod = importlib.import_module("msc-project_b200.dist")
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    system = pkg.make_ring(30, kind="coil", laps=2, lap_gap=9.0)
+    b = OracleBackend(po, system)
+    sh = dmod.ShardedEngine(b, dist, system.n, rank, world)
+    npairs = sh.build_pairlist()
+    sh.step(2, 0)
+    sh.merge()
+    sh.finish()
+    b._pull()
+    c, v = b.o.get_state()
+    if rank == 0:
+        q.put((npairs, c, v, (sh.plan.t0, sh.plan.t1, sh.plan.p0, sh.plan.p1)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_protocol_world2_equals_single_rank(edmd, po):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    npairs, c, v, plan = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    system = edmd.make_ring(30, kind="coil", laps=2, lap_gap=9.0)
+    o = po.Oracle(system, "port")
+    assert o.build_pairs() == npairs
+    o.step(2); o.merge()
+    co, vo = o.get_state()
+    assert np.array_equal(c, co) and np.array_equal(v, vo)
+    assert plan == (0, 15, 0, (npairs + 1) // 2)
+
+
+def test_shard_plan_covers_everything_once(edmd):
+    dmod = importlib.import_module("msc-project_b200.dist")
+    for n, npairs, world in ((1000, 494500, 8), (90, 450, 4), (1000, 494500, 3), (7, 5, 8), (10, 0, 2)):
+        seen_t = np.zeros(n, int); seen_p = np.zeros(npairs, int)
+        for r in range(world):
+            pl = dmod.ShardPlan(n, npairs, world, r)
+            seen_t[pl.t0:pl.t1] += 1; seen_p[pl.p0:pl.p1] += 1
+            assert pl.t1 - pl.t0 <= pl.t_chunk and pl.p1 - pl.p0 <= pl.p_chunk
+        assert np.all(seen_t == 1) and np.all(seen_p == 1)

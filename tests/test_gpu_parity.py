@@ -82,8 +82,8 @@ def test_nb_forces_bitwise(edmd, po, coil, krep, qfac):
     else:
         assert np.count_nonzero(np.abs(fo["nb"]) < 1.0) > 1000
     # shaken coordinates agree to 1e-10, so NB forces agree to a looser tolerance ...
-    assert rel(fg["nb"], fo["nb"]) < 1e-7
-    assert rel(fg["nb_energy"], fo["nb_energy"]) < 1e-7
+    assert rel(fg["nb"], fo["nb"]) < TOL
+    assert rel(fg["nb_energy"], fo["nb_energy"]) < TOL
     # ... and bit-for-bit when both start from the SAME coordinates:
     crd, _ = g.get_state()
     pairs = g.get_pairlist()
@@ -159,8 +159,8 @@ def test_trajectory(edmd, po, coil, random_on):
         (co, vo), (cg, vg) = o.get_state(), g.get_state()
         worst = max(worst, rel(cg, co), rel(vg, vo))
     # The 60-tetrad double coil is deliberately violent (interpenetrating helices, forces at the
-    # clip, stiff soft-core): NB forces amplify 1e-11 A differences of the shaken coordinates.
-    assert worst < 1e-9
+    # clip, stiff soft-core); measured growth: 1e-12 after 10 steps (tools/probe_growth.py).
+    assert worst < TOL
     o.merge(); g.merge()
     assert rel(g.get_state()[0], o.get_state()[0]) < TOL
     eo, eg = o.energies(), g.energies()
@@ -174,5 +174,5 @@ def test_gc90_shipped_config_block(edmd, po, gc90):
     o.step(20); g.step(20)
     o.merge(); g.merge()
     (co, vo), (cg, vg) = o.get_state(), g.get_state()
-    assert rel(cg, co) < TOL and rel(vg, vo) < 1e-8
-    assert np.allclose(g.energies(), o.energies(), rtol=1e-8)
+    assert rel(cg, co) < TOL and rel(vg, vo) < TOL
+    assert np.allclose(g.energies(), o.energies(), rtol=1e-10)

@@ -1,0 +1,168 @@
+"""CPU tests that pin the oracle (no GPU needed).
+
+1. port (oracle/edmd_oracle.c) == reference build (unmodified reference sources), bit for bit,
+   when oracle/_ref is present (it is built wherever /root/reference exists);
+2. port == tests/golden/*.npz (generated from the reference build by tests/golden/make_golden.py);
+3. the reference's own known answers: gamfac = 0.9960 (edmd.cpp:298) and
+   sum(noise_Factor) = 3594.75 at gamma = 2.0 (edmd.cpp:182) within the 0.1 % the missing
+   .prm's masses allow;
+4. glibc rand()/srand() restatement == this machine's libc;
+5. mathematical invariants: QCP rotations, Newton's third law, merge idempotence.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+STRIDE = 7
+T0 = 1000000000
+
+
+def _run_like_golden(po, system, kind, rng_calls_before):
+    out = {}
+    o = po.Oracle(system, kind)
+    out["npairs"] = np.array([o.build_pairs()]); out["pairs"] = o.get_pairs()
+    o.forces(random_on=False)
+    f = o.get_forces(); c, v = o.get_state()
+    out.update(f1_ed=f["ed"], f1_ed_energy=f["ed_energy"], f1_nb=f["nb"], f1_nb_energy=f["nb_energy"], f1_crd=c)
+    o.update_velocities(); o.update_coordinates()
+    c, v = o.get_state()
+    out.update(s1_crd=c, s1_vel=v, s1_temp=o.get_forces()["temperature"])
+    o.step(4); o.merge()
+    c, v = o.get_state()
+    out.update(s5m_crd=c, s5m_vel=v, s5m_energies=o.energies())
+    o2 = po.Oracle(system, kind); o2.set_time(T0)
+    if kind == "port":
+        o2.set_rng_calls(rng_calls_before)
+    o2.build_pairs(); o2.step(3, random_on=True)
+    c, v = o2.get_state()
+    out.update(r3_crd=c, r3_vel=v, r3_rnd=o2.get_forces()["rnd"])
+    return out
+
+
+@pytest.mark.parametrize("name", ["gc90", "coil40"])
+def test_port_matches_golden_vectors(edmd, po, name):
+    system = edmd.make_gc90() if name == "gc90" else edmd.make_ring(40, kind="coil", laps=2, lap_gap=9.0)
+    gold = np.load(os.path.join(GOLD, f"golden_{name}.npz"))
+    got = _run_like_golden(po, system, "port", int(gold["rng_calls_before"][0]))
+    for k, v in got.items():
+        v = np.asarray(v)
+        if v.ndim == 1 and v.size > 1000:
+            assert np.array_equal(v[::STRIDE], gold[k]), k
+            assert v.sum() == gold[k + "_sum"][0], k
+        else:
+            assert np.array_equal(v, gold[k]), k
+
+
+def test_port_is_bit_identical_to_reference_build(edmd, po, have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    system = edmd.make_ring(40, kind="coil", laps=2, lap_gap=12.0)
+    res = {}
+    for kind in ("port", "reference"):
+        o = po.Oracle(system, kind); o.set_time(T0)
+        calls = o.rng_calls()
+        if kind == "reference":
+            ref_calls = calls
+        o.build_pairs()
+        res[kind] = (o, calls)
+    # align the port's RNG_Seed counter with however many calls the reference library has made
+    res["port"][0].set_rng_calls(ref_calls)
+    outs = {}
+    for kind in ("port", "reference"):
+        o = res[kind][0]
+        o.step(3, random_on=True); o.merge()
+        c, v = o.get_state(); f = o.get_forces()
+        outs[kind] = dict(crd=c, vel=v, pairs=o.get_pairs(), energies=o.energies(), **f)
+    for k in outs["port"]:
+        assert np.array_equal(outs["port"][k], outs["reference"][k]), k
+
+
+def test_reference_comment_known_answers(edmd, po):
+    s = edmd.make_gc90()
+    dt, gamma = s.params[0], s.params[1]
+    assert round(1.0 / (1.0 + gamma * dt), 4) == 0.9960                 # edmd.cpp:298
+    m3 = s.psets[0].masses3
+    noise = np.sqrt(2.0 * gamma * s.params[4] * m3 / dt)                # edmd.cpp:184
+    assert abs(noise.sum() - 3594.75) / 3594.75 < 1e-3                  # edmd.cpp:182
+
+
+def test_glibc_rand_restatement_matches_libc(po):
+    libc = ctypes.CDLL("libc.so.6")
+    libc.rand.restype = ctypes.c_int
+    for seed in (1, 13581, 1000013580, 4000000000, 0):
+        libc.srand(ctypes.c_uint(seed))
+        want = np.array([libc.rand() for _ in range(500)], dtype=np.int32)
+        assert np.array_equal(po.glibc_rand_stream(seed, 500), want), seed
+
+
+def test_qcp_invariants(edmd, po):
+    s = edmd.make_gc90()
+    o = po.Oracle(s, "port")
+    rng = np.random.default_rng(1)
+    ref = s.psets[0].avg.reshape(-1, 3)
+    rot, rms = o.qcp(ref, ref)
+    assert np.allclose(rot, np.eye(3), atol=1e-12) and rms < 1e-6
+    for _ in range(5):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        moved = ref @ q.T + rng.normal(size=3) * 10
+        rot, rms = o.qcp(ref, moved)
+        assert np.allclose(rot @ rot.T, np.eye(3), atol=1e-12)
+        assert abs(np.linalg.det(rot) - 1.0) < 1e-12
+        assert np.allclose(rot, q.T, atol=1e-9)        # rot rotates `moved` back onto `ref`
+        assert rms < 1e-5
+
+
+def test_nb_pair_newton_third_law_and_double_counted_energy(edmd, po):
+    s = edmd.make_ring(40, kind="coil", laps=2, lap_gap=9.0)
+    o = po.Oracle(s, "port"); o.build_pairs()
+    off = s.off3
+    hits = 0
+    for t1, t2 in o.get_pairs()[:200]:
+        o.nb_forces_pair(int(t1), int(t2))
+        f = o.get_forces()
+        f1 = f["nb"][off[t1]:off[t1 + 1]].reshape(-1, 3); f2 = f["nb"][off[t2]:off[t2 + 1]].reshape(-1, 3)
+        assert np.allclose(f1.sum(0), -f2.sum(0), rtol=1e-9, atol=1e-9)
+        assert np.array_equal(f["nb_energy"][t1], f["nb_energy"][t2])   # edmd.cpp:282-283
+        hits += int(np.any(f1 != 0))
+    assert hits > 0
+
+
+def test_merge_averages_and_is_idempotent(edmd, po):
+    s = edmd.make_gc90()
+    rng = np.random.default_rng(2)
+    o = po.Oracle(s, "port")
+    o.set_state(s.crd + rng.normal(scale=0.1, size=s.crd.size), rng.normal(size=s.crd.size))
+    o.merge()
+    c1, v1 = o.get_state()
+    x = c1.reshape(s.n, 4, 63, 3)
+    for t in range(s.n):                      # overlapping copies agree after the merge
+        u = (t + 1) % s.n
+        assert np.array_equal(x[t, 1:], x[u, :3]) or t == s.n - 1
+    assert np.array_equal(x[s.n - 1, 1:], x[0, :3])     # ring closure, master.cpp:365-369
+    o.merge()
+    c2, v2 = o.get_state()
+    assert np.allclose(c2, c1, rtol=0, atol=1e-13) and np.allclose(v2, v1, rtol=0, atol=1e-13)
+
+
+def test_pair_list_predicate_gc90(edmd, po):
+    s = edmd.make_gc90()
+    o = po.Oracle(s, "port")
+    assert o.build_pairs() == 450                       # SURVEY.md §8a a-PL
+    p = o.get_pairs()
+    sep = np.abs(p[:, 0] - p[:, 1]); sep = np.minimum(sep, s.n - sep)
+    assert sep.min() == 6 and sep.max() == 10
+    odd = (np.abs(p[:, 0] - p[:, 1]) % 2) == 1
+    assert np.all(p[odd, 0] > p[odd, 1]) and np.all(p[~odd, 0] < p[~odd, 1])   # master.cpp:197-201
+    assert np.all(np.bincount(p.reshape(-1), minlength=s.n) == 10)
+
+
+def test_multithreaded_baseline_matches_serial(edmd, po):
+    s = edmd.make_ring(40, kind="coil", laps=2, lap_gap=9.0)
+    a = po.Oracle(s, "port"); a.build_pairs(); a.step(2, nthreads=1)
+    b = po.Oracle(s, "port"); b.build_pairs(); b.step(2, nthreads=4)
+    assert np.allclose(a.get_state()[0], b.get_state()[0], rtol=1e-12, atol=1e-12)
