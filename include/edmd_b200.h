@@ -76,6 +76,12 @@ int  edmd_set_params(edmd_engine* e, const edmd_params* p);
  * that electrostatics can be switched on (qfac = 332.064/4 per the comment at :240). */
 int  edmd_set_nb_consts(edmd_engine* e, double krep, double qfac);
 
+/* Arithmetic form of the NB distance pass (nb_scan_kernel): 0 = direct differences exactly
+ * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (default; 4 instead of
+ * 6 FP64 instructions per atom pair).  The pass only selects tetrad pairs for the exact
+ * force kernel, so forces and energies are bit-identical in both modes. */
+int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
+
 /* ---- data in / out ----------------------------------------------------------------- */
 /* Replaces Master::send_Tetrads / Worker::recv_Tetrads (master.cpp:137-153, MPI_Tetrad
  * datatype mpilib.cpp:23-62): uploads avg, masses, abq, eigenvalues, eigenvectors of n

@@ -105,7 +105,7 @@ struct edmd_engine {
     int rank = 1;
     long calls = 0;
 
-    int scan_grid = 592;
+    int scan_mode = 1;   // 0 direct, 1 gram (see nb.cu)
     cudaEvent_t span0 = nullptr, span1 = nullptr;   // edmd_timer_start/stop
     bool timing = false;
     Timer timers[T_COUNT];
@@ -238,7 +238,7 @@ int do_ed(edmd_engine* e) {
 int do_scan(edmd_engine* e) {
     timer_begin(e, T_SCAN);
     CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, e->d_hit, e->p0, e->p1, e->S,
-                      nb_effective_cut2(e->sp), e->scan_grid, e->st));
+                      nb_effective_cut2(e->sp), e->scan_mode, e->sms, e->st));
     timer_end(e, T_SCAN, e->p1 > e->p0 ? 1 : 0);
     e->hits_valid = true;
     return 0;
@@ -321,7 +321,6 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
         e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
         e->sp.mole_least = p->mole_Least;
     }
-    e->scan_grid = e->sms * 4;
     *out = e;
     return 0;
 }
@@ -349,6 +348,13 @@ int edmd_set_nb_consts(edmd_engine* e, double krep, double qfac) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->sp.krep = krep; e->sp.qfac = qfac;
     e->hits_valid = false;
+    return 0;
+}
+
+int edmd_set_nb_scan_mode(edmd_engine* e, int mode) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    if (mode != 0 && mode != 1) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram)", mode);
+    e->scan_mode = mode;
     return 0;
 }
 

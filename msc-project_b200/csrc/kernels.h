@@ -18,7 +18,7 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, double* c
                              double* e_ed, double* sup, int t0, int count, double scaled, cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
-                           long long p0, long long p1, int S, double cut2_eff, int grid, cudaStream_t st);
+                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms, cudaStream_t st);
 
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,

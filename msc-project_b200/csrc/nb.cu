@@ -7,14 +7,16 @@
 // Two kernels:
 //
 //  nb_scan_kernel — the FP64 hot loop.  For every listed tetrad pair it evaluates the squared
-//    distance of all num_Atoms x num_Atoms atom pairs exactly as edmd.cpp:251-256 does
-//    (3 DADD + DMUL + 2 DFMA per atom pair, the 9 algorithmic flops of SURVEY.md §8d) and
-//    records whether ANY atom pair can contribute (r^2 below the effective cutoff).  Thread a
-//    holds atom a of one tetrad in registers; the other tetrad's SoA planes sit in shared memory
-//    and are read as 128-bit broadcasts (two atoms per LDS).  The cutoff test is an integer
-//    min over the high words of r^2 (r^2 >= 0, so the IEEE bit pattern is monotonic) on the ALU
-//    pipe, leaving the FP64 pipe only the distance arithmetic.  Output: one byte per pair.
-//    Roofline: FP64 pipe.
+//    distance of all num_Atoms x num_Atoms atom pairs (the 9 algorithmic flops per atom pair
+//    of edmd.cpp:251-256) and records whether ANY atom pair can contribute
+//    (r^2 below the effective cutoff).  A CTA of 64 threads owns one tetrad pair at a time; each
+//    thread holds 4 atoms of one tetrad in registers; the other tetrad's SoA planes sit in
+//    shared memory (the next partner's 6 KB block is fetched by ONE TMA bulk copy —
+//    cp.async.bulk + mbarrier — while the current pair is computed) and are read as 128-bit
+//    broadcasts (two atoms per LDS), software-pipelined one step ahead.  The cutoff test is an
+//    integer min over the high words of r^2 (r^2 >= 0, so the IEEE bit pattern is monotonic) on
+//    the ALU pipe, leaving the FP64 pipe only the distance arithmetic.  Output: one byte per
+//    pair.  Roofline: FP64 pipe.
 //
 //  nb_accumulate_kernel — one CTA per tetrad walks that tetrad's partners in pair-list order
 //    and, for flagged pairs only, re-evaluates the pair with the reference's exact expression
@@ -37,68 +39,208 @@ struct ScanArgs {
     const double* crd;      // [n][3][S]
     const int* natoms;      // [n] atoms per tetrad
     const int2* pairs;      // [np] (t1, t2)
-    unsigned char* hit;     // [np]
+    unsigned char* hit;     // [np], zeroed before the launch; set to 1 by any warp that sees a hit
     long long p0, p1;       // this launch covers pairs [p0, p1)
     int S;
-    int hi_cut;             // high word of the effective squared cutoff
+    int hi_cut;             // high word of the effective squared cutoff (MODE 0)
+    int chunk;              // pairs per CTA
+    double cut;             // effective squared cutoff (MODE 1)
 };
 
-// smem: x,y,z planes of the streamed tetrad, padded to an even atom count.
-__global__ void __launch_bounds__(kThreads, 4) nb_scan_kernel(ScanArgs A) {
-    __shared__ __align__(16) double sx[kMaxStride];
-    __shared__ __align__(16) double sy[kMaxStride];
-    __shared__ __align__(16) double sz[kMaxStride];
-    const int tid = threadIdx.x;
+constexpr int kScanThreads = 64;                       // one CTA = one tetrad pair at a time
+constexpr int kTI = kMaxStride / kScanThreads;         // 4 register-resident atoms per thread
+
+// MODE 0 "direct": r^2 = (xi-xj)^2 + (yi-yj)^2 + (zi-zj)^2 exactly as edmd.cpp:251-256 —
+//   3 DADD + DMUL + 2 DFMA per atom pair.
+// MODE 1 "gram":   both tetrads are shifted to a pair-local origin o (atom 0 of the register-side
+//   tetrad) and the test r^2 < cut is rewritten, with x' = x - o and a bias B = 2^14, as
+//       c_ij = (|xj'|^2 + B) - 2 xi'.xj'   <   (cut + B) - |xi'|^2 = thr_i
+//   c_ij is a chain of 3 DFMA with (-2 xi') in registers and (xj', |xj'|^2 + B) in shared
+//   memory: the same 9 algorithmic flops in 3 FP64-pipe instructions.  c_ij = r^2 - |xi'|^2 + B
+//   is positive whenever |xi'|^2 < B (|xi'| < 128 A; a thread that sees a larger value flags
+//   the pair unconditionally), so the high-word integer test applies: hi(c) <= hi(thr_i) + 1.
+//   Rounding error of the chain <= 2^-51 (|xi'|+|xj'|)^2 + 2^-51 B ~ 1e-11, slack of the test
+//   >= 2^-20 thr_i >= 2e-6: a superset of the true hits, always.
+//   Either way the scan only SELECTS pairs: the forces come from nb_accumulate_kernel's exact
+//   arithmetic, so both modes give bit-identical results.
+//
+// Instruction-issue budget (measured on B200: an FP64 warp instruction holds the dispatch port
+// for 2 cycles): per atom pair MODE 0 issues 6 FP64 + 0.375 LDS.128 + 0.5 VIMNMX3, MODE 1 issues
+// 3 FP64 + 0.5 LDS.128 + 0.5 VIMNMX3 — the 4-atom register tile is what keeps the non-FP64 share
+// small (the first version of this kernel, 1 atom per thread, was dispatch-bound at 80 % FP64).
+// ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) ------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one contiguous global->shared bulk copy (UBLKCP), completion signalled on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes,
+                                            unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
+    constexpr int NP = MODE == 1 ? 4 : 3;                // planes staged per tetrad
+    constexpr double kBias = 16384.0;                    // B, see above
+    __shared__ __align__(16) double sb[2][NP][kMaxStride + 2];   // staged partner, double-buffered (+2: prefetch overrun)
+    __shared__ __align__(128) double raw[3 * kMaxStride];    // TMA landing zone: next partner's x|y|z planes
+    __shared__ __align__(8) unsigned long long bar;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int S = A.S;
 
-    for (long long p = A.p0 + blockIdx.x; p < A.p1; p += gridDim.x) {
-        const int2 pr = A.pairs[p];
-        // r^2 is symmetric: keep the lower-numbered tetrad in registers, stream the other.
+    // a short contiguous chunk of the pair list per CTA (the register-side tetrad — the lower
+    // index, i.e. the row of the i-major list — rarely changes inside a chunk); many more CTAs
+    // than SM slots, so the hardware block scheduler balances the tail dynamically
+    const long long chunk = A.chunk;
+    const long long k0 = A.p0 + chunk * blockIdx.x;
+    const long long k1 = (k0 + chunk < A.p1) ? k0 + chunk : A.p1;
+    if (k0 >= k1) return;
+    const unsigned plane_bytes = 3u * (unsigned)S * 8u;  // one tetrad = one contiguous block
+
+    double xi[kTI], yi[kTI], zi[kTI];                    // MODE 1: -2x', -2y', -2z'
+    int hthr[kTI];                                       // MODE 1: hi(thr_i) + 1, or -1 for a padding atom
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    int cur_r = -1;
+    bool wild = false;                                   // MODE 1: |xi'| too large for the error bound
+
+    int2 pr = A.pairs[k0];
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        const int ts0 = pr.x < pr.y ? pr.y : pr.x;
+        tma_load_1d(raw, A.crd + (size_t)ts0 * 3 * S, plane_bytes, &bar);
+    }
+    __syncthreads();                                     // barrier initialised before anyone waits
+
+    int b = 0;
+    unsigned phase = 0;
+    for (long long k = k0; k < k1; k++, b ^= 1, phase ^= 1) {
         const int tr = pr.x < pr.y ? pr.x : pr.y;
-        const int ts = pr.x < pr.y ? pr.y : pr.x;
-        const int nr = A.natoms[tr], ns = A.natoms[ts];
-        const double* Xr = A.crd + (size_t)tr * 3 * S;
-        const double* Xs = A.crd + (size_t)ts * 3 * S;
+        const int ns = A.natoms[pr.x < pr.y ? pr.y : pr.x];
+        int2 pr_next = pr;
+        if (k + 1 < k1) pr_next = A.pairs[k + 1];
+        if (tr != cur_r) {                               // new row: reload the register tile
+            cur_r = tr;
+            const double* Xr = A.crd + (size_t)tr * 3 * S;
+            const int nr = A.natoms[tr];
+            if (MODE == 1) { ox = Xr[0]; oy = Xr[S]; oz = Xr[2 * S]; wild = false; }
+#pragma unroll
+            for (int r = 0; r < kTI; r++) {
+                const int a = tid + kScanThreads * r;
+                if (a < nr) {
+                    const double x = Xr[a], y = Xr[S + a], z = Xr[2 * S + a];
+                    if (MODE == 1) {
+                        const double lx = x - ox, ly = y - oy, lz = z - oz;
+                        xi[r] = -2.0 * lx; yi[r] = -2.0 * ly; zi[r] = -2.0 * lz;
+                        const double w = fma(lz, lz, fma(ly, ly, lx * lx));
+                        wild = wild || !(w < 0.99 * kBias);
+                        hthr[r] = hi_word((A.cut + kBias) - w) + 1;
+                    } else { xi[r] = x; yi[r] = y; zi[r] = z; }
+                } else if (MODE == 1) { xi[r] = yi[r] = zi[r] = 0.0; hthr[r] = -1; }
+                else { xi[r] = yi[r] = zi[r] = -1e150; }
+            }
+        }
+        // stage the partner that the TMA engine delivered during the previous pair's arithmetic
+        mbar_wait(&bar, phase);
         const int ns2 = (ns + 1) & ~1;
-
-        double xi = 0.0, yi = 0.0, zi = 0.0;
-        if (tid < nr) { xi = Xr[tid]; yi = Xr[S + tid]; zi = Xr[2 * S + tid]; }
-        if (tid < ns2) {
-            const bool real = tid < ns;
-            sx[tid] = real ? Xs[tid] : 1e150;
-            sy[tid] = real ? Xs[S + tid] : 1e150;
-            sz[tid] = real ? Xs[2 * S + tid] : 1e150;
+#pragma unroll
+        for (int r = 0; r < kTI; r++) {
+            const int a = tid + kScanThreads * r;
+            if (a < ns2) {
+                const bool real = a < ns;
+                const double rx = raw[a], ry = raw[S + a], rz = raw[2 * S + a];
+                if (MODE == 1) {
+                    const double lx = rx - ox, ly = ry - oy, lz = rz - oz;
+                    sb[b][0][a] = real ? lx : 0.0; sb[b][1][a] = real ? ly : 0.0; sb[b][2][a] = real ? lz : 0.0;
+                    sb[b][3][a] = real ? fma(lz, lz, fma(ly, ly, lx * lx)) + kBias : 1e300;
+                } else {
+                    sb[b][0][a] = real ? rx : 1e150; sb[b][1][a] = real ? ry : 1e150; sb[b][2][a] = real ? rz : 1e150;
+                }
+            }
         }
-        __syncthreads();
+        __syncthreads();   // staged[b] complete, raw fully consumed, staged[b] of pair k-2 no longer read
+        if (tid == 0 && k + 1 < k1) {                    // next partner lands while this pair is computed
+            const int tsn = pr_next.x < pr_next.y ? pr_next.y : pr_next.x;
+            tma_load_1d(raw, A.crd + (size_t)tsn * 3 * S, plane_bytes, &bar);
+        }
 
-        int m0 = 0x7fffffff, m1 = 0x7fffffff;
-#pragma unroll 4
+        int mm[kTI];
+#pragma unroll
+        for (int r = 0; r < kTI; r++) mm[r] = 0x7fffffff;
+        const double* bx = sb[b][0]; const double* by = sb[b][1]; const double* bz = sb[b][2];
+        const double* bw = sb[b][NP - 1];
+        // software-pipelined: operands of step j+2 are fetched before step j's arithmetic
+        double2 xs = *reinterpret_cast<const double2*>(bx), ys = *reinterpret_cast<const double2*>(by);
+        double2 zs = *reinterpret_cast<const double2*>(bz), ws = *reinterpret_cast<const double2*>(bw);
+#pragma unroll 2
         for (int j = 0; j < ns2; j += 2) {
-            const double2 xs = *reinterpret_cast<const double2*>(&sx[j]);
-            const double2 ys = *reinterpret_cast<const double2*>(&sy[j]);
-            const double2 zs = *reinterpret_cast<const double2*>(&sz[j]);
-            const double dx0 = xi - xs.x, dy0 = yi - ys.x, dz0 = zi - zs.x;
-            const double dx1 = xi - xs.y, dy1 = yi - ys.y, dz1 = zi - zs.y;
-            const double r0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
-            const double r1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
-            m0 = min(m0, hi_word(r0));
-            m1 = min(m1, hi_word(r1));
+            const double2 nxs = *reinterpret_cast<const double2*>(bx + j + 2);
+            const double2 nys = *reinterpret_cast<const double2*>(by + j + 2);
+            const double2 nzs = *reinterpret_cast<const double2*>(bz + j + 2);
+            double2 nws = ws;
+            if (MODE == 1) nws = *reinterpret_cast<const double2*>(bw + j + 2);
+            if (MODE == 1) {
+#pragma unroll
+                for (int r = 0; r < kTI; r++) {
+                    const double c0 = fma(xi[r], xs.x, fma(yi[r], ys.x, fma(zi[r], zs.x, ws.x)));
+                    const double c1 = fma(xi[r], xs.y, fma(yi[r], ys.y, fma(zi[r], zs.y, ws.y)));
+                    mm[r] = min(mm[r], min(hi_word(c0), hi_word(c1)));
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < kTI; r++) {
+                    const double dx0 = xi[r] - xs.x, dy0 = yi[r] - ys.x, dz0 = zi[r] - zs.x;
+                    const double dx1 = xi[r] - xs.y, dy1 = yi[r] - ys.y, dz1 = zi[r] - zs.y;
+                    const double r0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+                    const double r1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+                    mm[r & 1] = min(mm[r & 1], min(hi_word(r0), hi_word(r1)));
+                }
+            }
+            xs = nxs; ys = nys; zs = nzs; ws = nws;
         }
-        const int pred = (tid < nr) && (min(m0, m1) <= A.hi_cut);
-        const int any = __syncthreads_or(pred);   // also fences smem reuse for the next pair
-        if (tid == 0) A.hit[p] = any ? 1 : 0;
+        bool pred = false;
+        if (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < kTI; r++) pred = pred || (mm[r] <= hthr[r]);
+            pred = pred || wild;
+        } else {
+            pred = min(mm[0], mm[1]) <= A.hi_cut;
+        }
+        if (__any_sync(0xffffffffu, pred) && lane == 0) A.hit[k] = 1;
+        pr = pr_next;
     }
 }
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
-                           long long p0, long long p1, int S, double cut2_eff, int grid, cudaStream_t st) {
+                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
-    long long want = p1 - p0;
-    if (want < grid) grid = (int)want;
+    cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
+    if (err != cudaSuccess) return err;
+    const long long want = p1 - p0;
+    long long chunk = want / ((long long)sms * 64);      // >= 64 chunks per SM when there is enough work
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8) chunk = 8;
+    const int grid = (int)((want + chunk - 1) / chunk);
     // hi-word test: r^2 < cut  ==>  hi(r^2) <= hi(cut); a superset, re-checked exactly later.
     long long bits; memcpy(&bits, &cut2_eff, 8);
-    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32)};
-    nb_scan_kernel<<<grid, kThreads, 0, st>>>(A);
+    const bool gram = (mode == 1) && cut2_eff >= 1e-3 && cut2_eff < 1e6;
+    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)chunk, cut2_eff};
+    if (gram) nb_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(A);
+    else      nb_scan_kernel<0><<<grid, kScanThreads, 0, st>>>(A);
     return cudaGetLastError();
 }
 
