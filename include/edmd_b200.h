@@ -98,6 +98,12 @@ int edmd_get_forces(edmd_engine* e, edmd_tetrad* tets, int n);
 /* Overwrites the device force arrays (used to test update_Velocities in isolation). */
 int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n);
 
+/* Page-locked host memory for the caller's Tetrad arrays.  When the coordinates (velocities)
+ * of all tetrads lie back to back in one block, edmd_set_state/edmd_get_state copy straight
+ * between that block and the device; if the block is pinned the copy runs at full PCIe rate. */
+void* edmd_alloc_pinned(size_t bytes);
+void  edmd_free_pinned(void* p);
+
 /* Flat variants for callers that do not hold Tetrad structs: arrays are tetrad-
  * concatenated xyz-interleaved, tetrad t at 3*sum_{s<t} num_Atoms[s].  NULL = skip. */
 int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel);

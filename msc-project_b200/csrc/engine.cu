@@ -481,18 +481,38 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     return edmd_set_state(e, tets, n);
 }
 
+// True when field `which` (0 coordinates, 1 velocities) of all tetrads forms one dense block in
+// tetrad order (a caller that allocates its Tetrad arrays from one slab — the copy can then
+// skip the gather through the engine's staging buffer).
+static bool dense_field(const edmd_engine* e, const edmd_tetrad* tets, int which) {
+    const double* base = which ? tets[0].velocities : tets[0].coordinates;
+    for (int t = 1; t < e->n; t++) {
+        const double* p = which ? tets[t].velocities : tets[t].coordinates;
+        if (p != base + e->off3_h[t]) return false;
+    }
+    return true;
+}
+
 int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n) {
     if (int rc = check_ready(e, false)) return rc;
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_state: n=%d but engine holds %d tetrads", n, e->n);
     CK(cudaSetDevice(e->device));
-    for (int t = 0; t < n; t++) {
-        const size_t b = sizeof(double) * 3 * e->natoms_h[t];
-        memcpy(e->h_stage + e->off3_h[t], tets[t].coordinates, b);
-        memcpy(e->h_stage + e->total3 + e->off3_h[t], tets[t].velocities, b);
-    }
     timer_begin(e, T_LAYOUT);
-    if (int rc = stage_in(e, e->crd, 0)) return rc;
-    if (int rc = stage_in(e, e->vel, 1)) return rc;
+    for (int which = 0; which < 2; which++) {
+        double* planes = which ? e->vel : e->crd;
+        if (dense_field(e, tets, which)) {       // straight from the caller's memory (fast if pinned)
+            double* d = e->d_stage + (size_t)which * e->total3;
+            CK(cudaMemcpyAsync(d, which ? tets[0].velocities : tets[0].coordinates, sizeof(double) * e->total3,
+                               cudaMemcpyHostToDevice, e->st));
+            CK(launch_pack_planes(d, e->d_off3, e->d_natoms, planes, e->n, e->S, e->st));
+            e->launches++;
+        } else {
+            for (int t = 0; t < n; t++)
+                memcpy(e->h_stage + (size_t)which * e->total3 + e->off3_h[t],
+                       which ? tets[t].velocities : tets[t].coordinates, sizeof(double) * 3 * e->natoms_h[t]);
+            if (int rc = stage_in(e, planes, which)) return rc;
+        }
+    }
     timer_end(e, T_LAYOUT, 0);
     CK(cudaStreamSynchronize(e->st));
     e->hits_valid = false;
@@ -503,13 +523,24 @@ int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
     if (int rc = check_ready(e, false)) return rc;
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_state: n mismatch");
     CK(cudaSetDevice(e->device));
-    if (int rc = stage_out(e, e->crd, 0)) return rc;
-    if (int rc = stage_out(e, e->vel, 1)) return rc;
+    bool dense[2];
+    for (int which = 0; which < 2; which++) {
+        dense[which] = dense_field(e, tets, which);
+        const double* planes = which ? e->vel : e->crd;
+        if (dense[which]) {
+            double* d = e->d_stage + (size_t)which * e->total3;
+            CK(launch_unpack_planes(planes, e->d_off3, e->d_natoms, d, e->n, e->S, e->st));
+            e->launches++;
+            CK(cudaMemcpyAsync(which ? tets[0].velocities : tets[0].coordinates, d, sizeof(double) * e->total3,
+                               cudaMemcpyDeviceToHost, e->st));
+        } else if (int rc = stage_out(e, planes, which)) return rc;
+    }
     CK(cudaStreamSynchronize(e->st));
-    for (int t = 0; t < n; t++) {
-        const size_t b = sizeof(double) * 3 * e->natoms_h[t];
-        memcpy(tets[t].coordinates, e->h_stage + e->off3_h[t], b);
-        memcpy(tets[t].velocities, e->h_stage + e->total3 + e->off3_h[t], b);
+    for (int which = 0; which < 2; which++) {
+        if (dense[which]) continue;
+        for (int t = 0; t < n; t++)
+            memcpy(which ? tets[t].velocities : tets[t].coordinates,
+                   e->h_stage + (size_t)which * e->total3 + e->off3_h[t], sizeof(double) * 3 * e->natoms_h[t]);
     }
     return 0;
 }
@@ -842,6 +873,13 @@ int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs) {
     if (flagged_pairs) *flagged_pairs = c;
     return 0;
 }
+
+void* edmd_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { fail(EDMD_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void edmd_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 int edmd_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
     int count = 0;

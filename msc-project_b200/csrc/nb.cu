@@ -47,8 +47,9 @@ struct ScanArgs {
     double cut;             // effective squared cutoff (MODE 1)
 };
 
-constexpr int kScanThreads = 64;                       // one CTA = one tetrad pair at a time
-constexpr int kTI = kMaxStride / kScanThreads;         // 4 register-resident atoms per thread
+constexpr int kScanThreads = 32;                       // one warp = one CTA = one tetrad pair at a time
+constexpr int kTI = kMaxStride / kScanThreads;         // 8 register-resident atoms per thread
+constexpr int kScanCtasPerSm = 12;
 
 // MODE 0 "direct": r^2 = (xi-xj)^2 + (yi-yj)^2 + (zi-zj)^2 exactly as edmd.cpp:251-256 —
 //   3 DADD + DMUL + 2 DFMA per atom pair.
@@ -94,10 +95,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(ScanArgs A) {
     constexpr int NP = MODE == 1 ? 4 : 3;                // planes staged per tetrad
     constexpr double kBias = 16384.0;                    // B, see above
-    __shared__ __align__(16) double sb[2][NP][kMaxStride + 2];   // staged partner, double-buffered (+2: prefetch overrun)
+    constexpr int NB = kScanThreads == 32 ? 1 : 2;       // a single warp needs no double buffer
+    __shared__ __align__(16) double sb[NB][NP][kMaxStride + 2];  // staged partner (+2: prefetch overrun)
     __shared__ __align__(128) double raw[3 * kMaxStride];    // TMA landing zone: next partner's x|y|z planes
     __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x, lane = tid & 31;
@@ -124,11 +126,11 @@ __global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
         const int ts0 = pr.x < pr.y ? pr.y : pr.x;
         tma_load_1d(raw, A.crd + (size_t)ts0 * 3 * S, plane_bytes, &bar);
     }
-    __syncthreads();                                     // barrier initialised before anyone waits
+    if (kScanThreads == 32) __syncwarp(); else __syncthreads();   // mbarrier initialised before anyone waits
 
     int b = 0;
     unsigned phase = 0;
-    for (long long k = k0; k < k1; k++, b ^= 1, phase ^= 1) {
+    for (long long k = k0; k < k1; k++, b ^= (NB - 1), phase ^= 1) {
         const int tr = pr.x < pr.y ? pr.x : pr.y;
         const int ns = A.natoms[pr.x < pr.y ? pr.y : pr.x];
         int2 pr_next = pr;
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
                 }
             }
         }
-        __syncthreads();   // staged[b] complete, raw fully consumed, staged[b] of pair k-2 no longer read
+        if (kScanThreads == 32) __syncwarp(); else __syncthreads();   // staged[b] complete, raw consumed
         if (tid == 0 && k + 1 < k1) {                    // next partner lands while this pair is computed
             const int tsn = pr_next.x < pr_next.y ? pr_next.y : pr_next.x;
             tma_load_1d(raw, A.crd + (size_t)tsn * 3 * S, plane_bytes, &bar);
@@ -194,12 +196,24 @@ __global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
             double2 nws = ws;
             if (MODE == 1) nws = *reinterpret_cast<const double2*>(bw + j + 2);
             if (MODE == 1) {
+                // r innermost at every chain level: consecutive DFMAs share the shared-memory
+                // operand (operand-reuse cache), so each reads only 2 registers from the RF — a DFMA
+                // with 3 distinct register sources is limited to one issue per 3 cycles
+                double c0[kTI], c1[kTI];
 #pragma unroll
-                for (int r = 0; r < kTI; r++) {
-                    const double c0 = fma(xi[r], xs.x, fma(yi[r], ys.x, fma(zi[r], zs.x, ws.x)));
-                    const double c1 = fma(xi[r], xs.y, fma(yi[r], ys.y, fma(zi[r], zs.y, ws.y)));
-                    mm[r] = min(mm[r], min(hi_word(c0), hi_word(c1)));
-                }
+                for (int r = 0; r < kTI; r++) c0[r] = fma(zi[r], zs.x, ws.x);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) c0[r] = fma(yi[r], ys.x, c0[r]);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) c0[r] = fma(xi[r], xs.x, c0[r]);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) c1[r] = fma(zi[r], zs.y, ws.y);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) c1[r] = fma(yi[r], ys.y, c1[r]);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) c1[r] = fma(xi[r], xs.y, c1[r]);
+#pragma unroll
+                for (int r = 0; r < kTI; r++) mm[r] = min(mm[r], min(hi_word(c0[r]), hi_word(c1[r])));
             } else {
 #pragma unroll
                 for (int r = 0; r < kTI; r++) {
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(kScanThreads, 8) nb_scan_kernel(ScanArgs A) {
         } else {
             pred = min(mm[0], mm[1]) <= A.hi_cut;
         }
-        if (__any_sync(0xffffffffu, pred) && lane == 0) A.hit[k] = 1;
+        if (__any_sync(0xffffffffu, pred) && lane == 0) A.hit[k] = 1;   // (also the WAR fence of the single buffer)
         pr = pr_next;
     }
 }

@@ -1,24 +1,29 @@
 // peak.cu — FP64 roofline denominator: DFMA issue-rate microbenchmark.
 //
 // MEASURED_PEAKS.json carries HBM and bf16 figures only, so the NB kernel's FP64 roofline is
-// measured here: every thread runs 8 independent DFMA chains (no memory traffic), 148 x 8 CTAs
-// of 256 threads.  2 flops per DFMA.  Reported next to an SM-clock estimate from clock64().
+// measured here: every thread runs 8 independent DFMA chains a_i = fma(a_i, b_i, c) (no memory
+// traffic), 148 x 8 CTAs of 256 threads, 2 flops per DFMA.  The operand pattern matters: a DFMA
+// with three distinct register sources issues at only ~76 % of this rate on B200
+// (tools/micro/dfma_rf.cu: 28.3 vs 37.1 TFLOP/s), so a pattern with two register sources and
+// one constant-bank source is used — the highest rate the pipe sustains.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace edmd {
 
-__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, long long* cycles) {
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, long long* cycles, double c) {
+    // a_i = fma(a_i, b_i, c): two register sources + one constant-bank source per DFMA
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
     double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-    const double m = 1.0000001, c = 1e-9;
+    const double b0 = 1.0 + 1e-9 * threadIdx.x, b1 = b0 + 1e-9, b2 = b0 + 2e-9, b3 = b0 + 3e-9;
+    const double b4 = b0 + 4e-9, b5 = b0 + 5e-9, b6 = b0 + 6e-9, b7 = b0 + 7e-9;
     const long long t0 = clock64();
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+            a0 = fma(a0, b0, c); a1 = fma(a1, b1, c); a2 = fma(a2, b2, c); a3 = fma(a3, b3, c);
+            a4 = fma(a4, b4, c); a5 = fma(a5, b5, c); a6 = fma(a6, b6, c); a7 = fma(a7, b7, c);
         }
     }
     const long long t1 = clock64();
@@ -40,7 +45,7 @@ cudaError_t measure_fp64_peak(double* tflops, double* sm_mhz_est) {
     for (int rep = 0; rep < 6; rep++) {
         cudaMemset(cyc, 0, sizeof(long long));
         cudaEventRecord(e0);
-        dfma_kernel<<<grid, 256>>>(out, iters, cyc);
+        dfma_kernel<<<grid, 256>>>(out, iters, cyc, 1e-9);
         cudaEventRecord(e1);
         err = cudaEventSynchronize(e1);
         if (err != cudaSuccess) break;

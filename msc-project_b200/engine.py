@@ -108,6 +108,8 @@ def load_library():
         "edmd_timing_reset": (C.c_int, [E]),
         "edmd_launch_count": (LL, [E]),
         "edmd_nb_stats": (C.c_int, [E, C.POINTER(LL)]),
+        "edmd_alloc_pinned": (C.c_void_p, [C.c_size_t]),
+        "edmd_free_pinned": (None, [C.c_void_p]),
         "edmd_measure_fp64_peak": (C.c_int, [C.c_int, PD, PD]),
     }
     for name, (res, args) in sig.items():
@@ -126,15 +128,28 @@ def _ptr(a: np.ndarray):
 class TetradBlock:
     """Host memory for n reference-layout Tetrad structs plus the arrays they point into."""
 
-    def __init__(self, sys: EdmdSystem):
+    def __init__(self, sys: EdmdSystem, pinned: bool = False):
         n = sys.n
         self.sys = sys
         na = sys.num_atoms.astype(np.int64)
         self.off3 = sys.off3
         n3 = 3 * na
-        self.crd = np.ascontiguousarray(sys.crd, dtype=np.float64).copy()
-        self.vel = np.ascontiguousarray(sys.vel, dtype=np.float64).copy()
         tot = int(self.off3[-1])
+        self._pinned = []
+        if pinned:      # coordinates / velocities in page-locked memory (edmd_alloc_pinned)
+            lib = load_library()
+            bufs = []
+            for _ in range(2):
+                p = lib.edmd_alloc_pinned(8 * tot)
+                if not p:
+                    raise EngineError(lib.edmd_last_error().decode())
+                self._pinned.append((lib, p))
+                bufs.append(np.ctypeslib.as_array(C.cast(p, PD), shape=(tot,)))
+            self.crd, self.vel = bufs
+            self.crd[:] = sys.crd; self.vel[:] = sys.vel
+        else:
+            self.crd = np.ascontiguousarray(sys.crd, dtype=np.float64).copy()
+            self.vel = np.ascontiguousarray(sys.vel, dtype=np.float64).copy()
         self.off_ed = self.off3 + np.arange(n + 1)          # 3N+1 per tetrad
         self.off_nb = self.off3 + 2 * np.arange(n + 1)      # 3N+2 per tetrad
         self.ed = np.zeros(tot + n)
@@ -168,6 +183,14 @@ class TetradBlock:
     def ptr(self):
         return C.c_void_p(self.structs.ctypes.data)
 
+    def __del__(self):
+        for lib, p in getattr(self, "_pinned", []):
+            try:
+                lib.edmd_free_pinned(p)
+            except Exception:
+                pass
+        self._pinned = []
+
     # views of the reference-layout force arrays
     def ed_forces(self):
         n = self.sys.n
@@ -184,8 +207,8 @@ class TetradBlock:
         return self.structs["temperature"].copy()
 
 
-def build_tetrads(sys: EdmdSystem) -> TetradBlock:
-    return TetradBlock(sys)
+def build_tetrads(sys: EdmdSystem, pinned: bool = False) -> TetradBlock:
+    return TetradBlock(sys, pinned)
 
 
 class Engine:
@@ -195,13 +218,13 @@ class Engine:
     T_ED, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT = range(8)
     BUF_CRD, BUF_VEL, BUF_FED, BUF_RND, BUF_FNB, BUF_HIT, BUF_CENTROID = range(7)
 
-    def __init__(self, sys: EdmdSystem, device: int = 0):
+    def __init__(self, sys: EdmdSystem, device: int = 0, pinned: bool = True):
         self.lib = load_library()
         self.h = C.c_void_p()
         p = Params(*[float(x) for x in sys.params])
         self._ck(self.lib.edmd_create(C.byref(p), device, C.byref(self.h)))
         self.sys = sys
-        self.block = build_tetrads(sys)
+        self.block = build_tetrads(sys, pinned)
         bp = None
         if sys.bp_atoms is not None:
             self._bp = np.ascontiguousarray(sys.bp_atoms, dtype=np.int32)
@@ -231,9 +254,16 @@ class Engine:
             self.block.vel[:] = vel
         self._ck(self.lib.edmd_set_state(self.h, self.block.ptr, self.sys.n))
 
-    def get_state(self):
+    def get_state(self, copy: bool = True):
+        """Device -> the host Tetrad arrays (self.block.crd / .vel); returns copies unless copy=False."""
         self._ck(self.lib.edmd_get_state(self.h, self.block.ptr, self.sys.n))
+        if not copy:
+            return self.block.crd, self.block.vel
         return self.block.crd.copy(), self.block.vel.copy()
+
+    def push_state(self):
+        """Host Tetrad arrays (self.block.crd / .vel, edited in place) -> device."""
+        self._ck(self.lib.edmd_set_state(self.h, self.block.ptr, self.sys.n))
 
     def get_forces(self):
         """dict(ed, ed_energy, rnd, nb, nb_energy[n,2], temperature) via the Tetrad structs."""
