@@ -42,12 +42,19 @@ def load_pkg():
 
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def start(self):
         try:
@@ -72,17 +79,27 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        import datetime
+        all_sm = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx = float(f[2])
+                v_sm = float(f[1]); mx = float(f[2])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
             except ValueError:
                 continue
+            all_sm.append(v_sm)
+            # keep the samples taken inside the timed region (100 ms slack for the sampling period)
+            if self.t_begin and self.t_end and not (self.t_begin - 0.1 <= ts <= self.t_end + 0.1):
+                continue
+            sm.append(v_sm)
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
+        if not sm:
+            sm = all_sm
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
@@ -159,7 +176,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline sampling (rank 0, N=1)")
@@ -202,6 +219,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # started early: nvidia-smi needs ~100 ms before its first sample
     for _ in range(warmup):
         sh.step(1, 0)
         with backend.stream_ctx():
@@ -210,20 +230,19 @@ def main():
 
     # ---- timed region: K steps, device time by CUDA events on the engine stream, L2 flushed
     # (256 MB fill) between steps outside the event pairs ------------------------------------
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     g.timing(True); g.timing_reset()
     launches0 = g.launch_count
     barrier()
-    step_ms = []
-    for _ in range(args.steps):
-        g.timer_start()
+    sampler.mark_begin()
+    for k in range(args.steps):      # nothing in this loop blocks the host: the GPU queue stays full
+        g.mark(2 * k)
         sh.step(1, 0)
-        step_ms.append(g.timer_stop())
+        g.mark(2 * k + 1)
         with backend.stream_ctx():
-            flush.fill_(1)
+            flush.fill_(1)           # L2 flush, outside the (2k, 2k+1) event pair
     barrier()
+    step_ms = [g.mark_elapsed(2 * k, 2 * k + 1) for k in range(args.steps)]
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     launches = g.launch_count - launches0
     total_ms = sum(step_ms)

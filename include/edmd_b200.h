@@ -143,6 +143,9 @@ int edmd_nb_accumulate(edmd_engine* e);
 /* EDMD::update_Velocities (edmd.cpp:289-317) and EDMD::update_Coordinates (:322-327). */
 int edmd_update_velocities(edmd_engine* e);
 int edmd_update_coordinates(edmd_engine* e);
+/* edmd_nb_accumulate + edmd_integrate fused (the clipped force never leaves registers
+ * between the two); what edmd_step runs after the distance pass. */
+int edmd_nb_finish(edmd_engine* e);
 /* update_Velocity then update_Coordinate back to back (simulation.cpp:45-46) in one pass. */
 int edmd_integrate(edmd_engine* e);
 /* Master::merge_Vels_n_Crds (master.cpp:347-384). */
@@ -179,6 +182,10 @@ void* edmd_stream(edmd_engine* e);         /* the cudaStream_t all engine work r
  * stream (torch.cuda.Event would only see torch's current stream).  stop synchronises. */
 int edmd_timer_start(edmd_engine* e);
 int edmd_timer_stop(edmd_engine* e, double* ms);
+/* Non-blocking variant: record numbered marks (CUDA events) on the engine stream and read the
+ * device time between two of them later (edmd_mark_elapsed synchronises on slot_b). */
+int edmd_mark(edmd_engine* e, int slot);
+int edmd_mark_elapsed(edmd_engine* e, int slot_a, int slot_b, double* ms);
 /* Accumulated device time (ms) and launch count per kernel since the last reset, measured
  * with CUDA events on the engine stream.  which: 0 ED, 1 NB scan, 2 NB accumulate+clip,
  * 3 random, 4 merge, 5 pair list, 6 integrate, 7 layout (pack/unpack at the boundary). */

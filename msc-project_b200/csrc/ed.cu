@@ -225,7 +225,8 @@ __global__ void __launch_bounds__(kSupThreads) superpose_kernel(SupArgs A) {
 struct EdArgs {
     ParamSets ps;
     const int* param_id;
-    double* crd;         // [n][3][S] in/out (overwritten with the re-embedded coordinates)
+    const double* crd_in;  // [n][3][S] current coordinates
+    double* crd;         // [n][3][S] out: the re-embedded coordinates (may alias crd_in)
     double* fed;         // [n][3][S] out
     double* e_ed;        // [n] out
     const double* sup;   // [n][kSupWords] from superpose_kernel
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
     const int S = A.ps.S;
     const bool on = tid < na;
     double* X = A.crd + (size_t)t * 3 * S;
+    const double* XIN = A.crd_in + (size_t)t * 3 * S;
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
     const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
     const double* EL = A.ps.eval + (size_t)ps * A.ps.NEV;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
 
     double x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0;
     if (on) {
-        x0 = X[tid]; x1 = X[S + tid]; x2 = X[2 * S + tid];
+        x0 = XIN[tid]; x1 = XIN[S + tid]; x2 = XIN[2 * S + tid];
         a0 = AV[tid]; a1 = AV[S + tid]; a2 = AV[2 * S + tid];
     }
     double ev[kNevReg][3];
@@ -343,14 +345,14 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
     }
 }
 
-cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, double* crd, double* fed,
+cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                              double* e_ed, double* sup, int t0, int count, double scaled, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    SupArgs B{ps, param_id, crd, sup, t0};
+    SupArgs B{ps, param_id, crd_in, sup, t0};
     superpose_kernel<<<count, kSupThreads, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    EdArgs A{ps, param_id, crd, fed, e_ed, sup, t0, scaled};
+    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled};
     ed_project_kernel<<<count, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }

@@ -74,6 +74,8 @@ struct edmd_engine {
 
     // device: state planes
     double *crd = nullptr, *vel = nullptr, *fed = nullptr, *rnd = nullptr, *fnb = nullptr;
+    double* crd2 = nullptr;        // post-integrate coordinates written by the fused finish kernel
+    bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     bool rnd_zero = true;   // random terms currently all zero
 
@@ -107,6 +109,7 @@ struct edmd_engine {
 
     int scan_mode = 1;   // 0 direct, 1 gram (see nb.cu)
     cudaEvent_t span0 = nullptr, span1 = nullptr;   // edmd_timer_start/stop
+    std::vector<cudaEvent_t> marks;                 // edmd_mark / edmd_mark_elapsed
     bool timing = false;
     Timer timers[T_COUNT];
     long long launches = 0;
@@ -145,13 +148,14 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_natoms); cudaFree(e->d_param_id); cudaFree(e->d_ps_na); cudaFree(e->d_ps_nev);
     cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
     cudaFree(e->d_eval); cudaFree(e->d_evec);
-    cudaFree(e->crd); cudaFree(e->vel); cudaFree(e->fed); cudaFree(e->rnd); cudaFree(e->fnb);
+    cudaFree(e->crd); cudaFree(e->crd2); cudaFree(e->vel); cudaFree(e->fed); cudaFree(e->rnd); cudaFree(e->fnb);
     cudaFree(e->e_ed); cudaFree(e->e_nb); cudaFree(e->temp); cudaFree(e->cen); cudaFree(e->sup);
     cudaFree(e->d_stage); if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_row_count); cudaFree(e->d_row_off);
     cudaFree(e->d_adj_off); cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair); cudaFree(e->d_bp_off);
     e->d_natoms = e->d_param_id = e->d_ps_na = e->d_ps_nev = nullptr; e->d_off3 = nullptr;
     e->d_avg = e->d_mass = e->d_chg = e->d_eval = e->d_evec = nullptr;
+    e->crd2 = nullptr; e->latest_in_crd2 = false;
     e->crd = e->vel = e->fed = e->rnd = e->fnb = e->e_ed = e->e_nb = e->temp = e->cen = e->sup = nullptr;
     e->d_stage = nullptr; e->h_stage = nullptr;
     e->d_pairs = nullptr; e->d_hit = nullptr; e->d_row_count = e->d_row_off = e->d_adj_off = nullptr;
@@ -229,9 +233,21 @@ int check_ready(edmd_engine* e, bool need_pairs) {
     return 0;
 }
 
+// The fused finish kernel leaves the owned tetrads' new coordinates in crd2 (other CTAs may still
+// be reading crd).  The ED pass consumes them from there; every other consumer calls this first.
+int normalize(edmd_engine* e) {
+    if (!e->latest_in_crd2) return 0;
+    const size_t off = (size_t)e->t0 * 3 * e->S, cnt = (size_t)(e->t1 - e->t0) * 3 * e->S;
+    if (cnt) CK(cudaMemcpyAsync(e->crd + off, e->crd2 + off, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e->st));
+    e->latest_in_crd2 = false;
+    return 0;
+}
+
 int do_ed(edmd_engine* e) {
     timer_begin(e, T_ED);
-    CK(launch_ed_forces(e->ps, e->d_param_id, e->crd, e->fed, e->e_ed, e->sup, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
+    const double* src = e->latest_in_crd2 ? e->crd2 : e->crd;
+    e->latest_in_crd2 = false;
+    CK(launch_ed_forces(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -249,6 +265,17 @@ int do_accumulate(edmd_engine* e, int use_hits) {
                             e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
                             e->sp, use_hits, e->st));
     timer_end(e, T_ACC, 1);
+    return 0;
+}
+// accumulate + clip + velocity + coordinate update in one kernel (edmd_step, edmd_nb_finish)
+int do_finish(edmd_engine* e) {
+    if (int rc = normalize(e)) return rc;
+    timer_begin(e, T_ACC);
+    CK(launch_nb_finish(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off, e->d_adj_partner,
+                        e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
+                        e->rnd_zero ? nullptr : e->rnd, e->temp, e->t0, e->t1 - e->t0, e->S, e->sp, e->st));
+    timer_end(e, T_ACC, 1);
+    e->latest_in_crd2 = true;
     return 0;
 }
 int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before) {
@@ -331,6 +358,7 @@ void edmd_destroy(edmd_engine* e) {
     for (int i = 0; i < T_COUNT; i++) timer_fold(e, i);
     free_system(e);
     if (e->span0) { cudaEventDestroy(e->span0); cudaEventDestroy(e->span1); }
+    for (cudaEvent_t ev : e->marks) cudaEventDestroy(ev);
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -437,7 +465,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->d_avg, avg.size())); CK(dev_alloc(&e->d_mass, mass.size())); CK(dev_alloc(&e->d_chg, chg.size()));
     CK(dev_alloc(&e->d_eval, eval.size())); CK(dev_alloc(&e->d_evec, evec.size()));
     const size_t planes = (size_t)n * 3 * S;
-    CK(dev_alloc(&e->crd, planes)); CK(dev_alloc(&e->vel, planes)); CK(dev_alloc(&e->fed, planes));
+    CK(dev_alloc(&e->crd, planes)); CK(dev_alloc(&e->crd2, planes)); CK(dev_alloc(&e->vel, planes)); CK(dev_alloc(&e->fed, planes));
     CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
@@ -497,6 +525,7 @@ int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n) {
     if (int rc = check_ready(e, false)) return rc;
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_state: n=%d but engine holds %d tetrads", n, e->n);
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     timer_begin(e, T_LAYOUT);
     for (int which = 0; which < 2; which++) {
         double* planes = which ? e->vel : e->crd;
@@ -523,6 +552,7 @@ int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
     if (int rc = check_ready(e, false)) return rc;
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_state: n mismatch");
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     bool dense[2];
     for (int which = 0; which < 2; which++) {
         dense[which] = dense_field(e, tets, which);
@@ -548,6 +578,7 @@ int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
 int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     if (crd) { memcpy(e->h_stage, crd, sizeof(double) * e->total3); if (int rc = stage_in(e, e->crd, 0)) return rc; }
     if (vel) { memcpy(e->h_stage + e->total3, vel, sizeof(double) * e->total3); if (int rc = stage_in(e, e->vel, 1)) return rc; }
     CK(cudaStreamSynchronize(e->st));
@@ -558,6 +589,7 @@ int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel) {
 int edmd_get_state_flat(edmd_engine* e, double* crd, double* vel) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     if (crd) if (int rc = stage_out(e, e->crd, 0)) return rc;
     if (vel) if (int rc = stage_out(e, e->vel, 1)) return rc;
     CK(cudaStreamSynchronize(e->st));
@@ -624,6 +656,7 @@ int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n) {
 int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     const int n = e->n;
     const double cut2 = e->sp.mole_cutoff * e->sp.mole_cutoff;
     timer_begin(e, T_PAIRS);
@@ -685,6 +718,8 @@ int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
     if (int rc = check_ready(e, false)) return rc;
     if (t0 < 0 || t1 > e->n || t0 > t1) return fail(EDMD_ERR_ARG, "tetrad shard [%d,%d) out of range", t0, t1);
     if (p0 < 0 || p0 > p1 || (e->have_pairs && p1 > e->np)) return fail(EDMD_ERR_ARG, "pair shard out of range");
+    CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     e->t0 = t0; e->t1 = t1; e->p0 = p0; e->p1 = p1; e->shard_pairs_custom = true;
     e->hits_valid = false;
     return 0;
@@ -706,18 +741,21 @@ int edmd_random_terms(edmd_engine* e, int mode, long time0, int rank, long calls
 int edmd_nb_scan(edmd_engine* e) {
     if (int rc = check_ready(e, true)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     return do_scan(e);
 }
 
 int edmd_nb_accumulate(edmd_engine* e) {
     if (int rc = check_ready(e, true)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     return do_accumulate(e, 1);
 }
 
 int edmd_nb_forces(edmd_engine* e) {
     if (int rc = check_ready(e, true)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     if (int rc = do_scan(e)) return rc;
     return do_accumulate(e, 1);
 }
@@ -731,13 +769,22 @@ int edmd_update_velocities(edmd_engine* e) {
 int edmd_update_coordinates(edmd_engine* e) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     e->hits_valid = false;
     return do_integrate(e, 0, 1);
+}
+
+int edmd_nb_finish(edmd_engine* e) {
+    if (int rc = check_ready(e, true)) return rc;
+    CK(cudaSetDevice(e->device));
+    e->hits_valid = false;
+    return do_finish(e);
 }
 
 int edmd_integrate(edmd_engine* e) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     e->hits_valid = false;
     return do_integrate(e, 1, 1);
 }
@@ -747,6 +794,7 @@ int edmd_merge(edmd_engine* e) {
     if (!e->have_bp) return fail(EDMD_ERR_STATE, "edmd_merge needs bp_atoms (pass it to edmd_upload_tetrads)");
     if (e->n < 4) return fail(EDMD_ERR_LIMIT, "merge needs at least 4 tetrads");
     CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     timer_begin(e, T_MERGE);
     CK(launch_merge(e->vel, e->crd, e->d_bp_off, e->n, e->S, e->st));
     timer_end(e, T_MERGE, 1);
@@ -785,8 +833,7 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
         if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls)) return rc;
         if (random_mode == 1) e->calls += e->n;
         if (int rc = do_scan(e)) return rc;
-        if (int rc = do_accumulate(e, 1)) return rc;
-        if (int rc = do_integrate(e, 1, 1)) return rc;
+        if (int rc = do_finish(e)) return rc;
     }
     e->hits_valid = false;
     return 0;
@@ -801,6 +848,8 @@ int edmd_sync(edmd_engine* e) {
 
 int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes) {
     if (int rc = check_ready(e, false)) return rc;
+    CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
     const size_t planes = sizeof(double) * (size_t)e->n * 3 * e->S;
     void* p = nullptr; size_t b = 0;
     switch (which) {
@@ -837,6 +886,24 @@ int edmd_timer_stop(edmd_engine* e, double* ms) {
     CK(cudaEventSynchronize(e->span1));
     float f = 0.f;
     CK(cudaEventElapsedTime(&f, e->span0, e->span1));
+    if (ms) *ms = f;
+    return 0;
+}
+
+int edmd_mark(edmd_engine* e, int slot) {
+    if (!e || slot < 0 || slot > 65535) return fail(EDMD_ERR_ARG, "bad mark slot");
+    CK(cudaSetDevice(e->device));
+    while ((int)e->marks.size() <= slot) { cudaEvent_t ev; CK(cudaEventCreate(&ev)); e->marks.push_back(ev); }
+    CK(cudaEventRecord(e->marks[slot], e->st));
+    return 0;
+}
+int edmd_mark_elapsed(edmd_engine* e, int slot_a, int slot_b, double* ms) {
+    if (!e || slot_a < 0 || slot_b < 0 || slot_a >= (int)e->marks.size() || slot_b >= (int)e->marks.size())
+        return fail(EDMD_ERR_ARG, "mark slot not recorded");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventSynchronize(e->marks[slot_b]));
+    float f = 0.f;
+    CK(cudaEventElapsedTime(&f, e->marks[slot_a], e->marks[slot_b]));
     if (ms) *ms = f;
     return 0;
 }

@@ -9,64 +9,21 @@
 // 48,384 algorithmic bytes per tetrad).  Roofline: HBM.
 #include "common.cuh"
 #include "kernels.h"
+#include "step_math.cuh"
 
 namespace edmd {
-
-struct IntArgs {
-    ParamSets ps;
-    const int* param_id;
-    double* vel;          // [n][3][S] in/out
-    double* crd;          // [n][3][S] in/out
-    const double* fed;    // [n][3][S]
-    const double* rnd;    // [n][3][S] or nullptr (= zero random terms)
-    const double* fnb;    // [n][3][S]
-    double* temp;         // [n] out
-    int t0;
-    int do_vel, do_crd;
-    double dt, gamma, tautp, scaled;
-};
 
 __global__ void __launch_bounds__(kThreads, 4) integrate_kernel(IntArgs A) {
     __shared__ double red[1][kWarps];
     const int t = A.t0 + blockIdx.x;
     const int tid = threadIdx.x;
-    const int ps = A.param_id[t];
-    const int na = A.ps.na[ps];
     const int S = A.ps.S;
-    const bool on = tid < na;
-    const size_t base = (size_t)t * 3 * S;
-    double v[3] = {0, 0, 0};
-    if (on) {
+    double f[3] = {0, 0, 0};
+    if (A.do_vel && tid < A.ps.na[A.param_id[t]]) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) v[c] = A.vel[base + c * S + tid];
+        for (int c = 0; c < 3; c++) f[c] = A.fnb[(size_t)t * 3 * S + c * S + tid];
     }
-    if (A.do_vel) {
-        const double gamfac = 1.0 / (1.0 + A.gamma * A.dt);
-        double ke[1] = {0.0};
-        if (on) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                const size_t k = base + c * S + tid;
-                const double m = A.ps.mass[(size_t)ps * 3 * S + c * S + tid];
-                const double r = A.rnd ? A.rnd[k] : 0.0;
-                // edmd.cpp:299 — note the ED force is not divided by the mass
-                v[c] = (v[c] + A.fed[k] * A.dt + (r + A.fnb[k]) * A.dt / m) * gamfac;
-                ke[0] += 0.5 * m * v[c] * v[c];
-            }
-        }
-        block_sum<1>(ke, red);
-        const double target = 0.5 * A.scaled * 3 * na;                              // :305
-        const double tscal = sqrt(1.0 + (A.dt / A.tautp) * ((target / ke[0]) - 1.0)); // :306
-        if (tid == 0) A.temp[t] = ke[0] * 2 / (0.002 * 3 * na) * (tscal * tscal);      // :309-310
-        if (on) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { v[c] *= tscal; A.vel[base + c * S + tid] = v[c]; }
-        }
-    }
-    if (A.do_crd && on) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) A.crd[base + c * S + tid] += v[c] * A.dt;        // :325
-    }
+    integrate_tetrad(A, t, f, red);
 }
 
 cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
@@ -74,7 +31,7 @@ cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* v
                              int t0, int count, int do_vel, int do_crd, const SimParams& sp,
                              cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    IntArgs A{ps, param_id, vel, crd, fed, rnd, fnb, temp, t0, do_vel, do_crd,
+    IntArgs A{ps, param_id, vel, crd, crd, fed, rnd, fnb, temp, t0, do_vel, do_crd,
               sp.dt, sp.gamma, sp.tautp, sp.scaled};
     integrate_kernel<<<count, kThreads, 0, st>>>(A);
     return cudaGetLastError();

@@ -14,7 +14,7 @@ inline double nb_effective_cut2(const SimParams& sp) {
 }
 
 constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scratch (ed.cu)
-cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, double* crd, double* fed,
+cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                              double* e_ed, double* sup, int t0, int count, double scaled, cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
@@ -24,6 +24,12 @@ cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,
                                  const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
                                  const SimParams& sp, int use_hits, cudaStream_t st);
+
+cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
+                             const unsigned char* hit, const long long* adj_off, const int* adj_partner,
+                             const int* adj_pair, double* fnb, double* e_nb, const ParamSets& ps, double* vel,
+                             double* crd_out, const double* fed, const double* rnd, double* temp, int t0, int count,
+                             int S, const SimParams& sp, cudaStream_t st);
 
 cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
                              const double* fed, const double* rnd, const double* fnb, double* temp,

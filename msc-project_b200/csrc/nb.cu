@@ -30,6 +30,7 @@
 // is therefore min(atom_Cutoff^2, 2.0) when qfac == 0 and atom_Cutoff^2 otherwise.
 #include "common.cuh"
 #include "kernels.h"
+#include "step_math.cuh"
 
 namespace edmd {
 
@@ -278,12 +279,16 @@ struct AccArgs {
     int use_hits;              // 0: treat every pair as flagged
 };
 
-__global__ void __launch_bounds__(kThreads, 2) nb_accumulate_kernel(AccArgs A) {
-    __shared__ double sx[kMaxStride], sy[kMaxStride], sz[kMaxStride], sq[kMaxStride];
-    __shared__ unsigned sFlag[kWarps];
-    __shared__ double red[2][kWarps];
+struct AccSmem {
+    double sx[kMaxStride], sy[kMaxStride], sz[kMaxStride], sq[kMaxStride];
+    unsigned sFlag[kWarps];
+    double red[2][kWarps];
+};
 
-    const int t = A.t0 + blockIdx.x;
+// Accumulates, clips and stores the NB force of tetrad t; leaves this thread's clipped force in f[].
+__device__ __forceinline__ void nb_accumulate_tetrad(const AccArgs& A, int t, AccSmem& sm, double f[3]) {
+    double* sx = sm.sx; double* sy = sm.sy; double* sz = sm.sz; double* sq = sm.sq;
+    unsigned* sFlag = sm.sFlag;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = A.S;
     const int na = A.natoms[t];
@@ -361,16 +366,37 @@ __global__ void __launch_bounds__(kThreads, 2) nb_accumulate_kernel(AccArgs A) {
 
     // clip (master.cpp:304-305) and store; energies are sums over this tetrad's atoms
     double* F = A.fnb + (size_t)t * 3 * S;
+    f[0] = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
+    f[1] = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
+    f[2] = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
     if (on) {
-        F[tid]         = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
-        F[S + tid]     = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
-        F[2 * S + tid] = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
+        F[tid] = f[0]; F[S + tid] = f[1]; F[2 * S + tid] = f[2];
     } else if (tid < S) {
         F[tid] = 0.0; F[S + tid] = 0.0; F[2 * S + tid] = 0.0;
     }
     double ev[2] = {E0, E1};
-    block_sum<2>(ev, red);
+    block_sum<2>(ev, sm.red);
     if (tid == 0) { A.e_nb[2 * (size_t)t] = ev[0]; A.e_nb[2 * (size_t)t + 1] = ev[1]; }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) nb_accumulate_kernel(AccArgs A) {
+    __shared__ AccSmem sm;
+    double f[3];
+    nb_accumulate_tetrad(A, A.t0 + blockIdx.x, sm, f);
+}
+
+// Fused tail of the step: NB accumulate + clip (master.cpp:297-322), then update_Velocities and
+// update_Coordinates (edmd.cpp:289-327) with the clipped force still in registers — the N x 3S
+// force array is written once for the caller (edmd_get_forces) but never read back.
+// Other CTAs read this tetrad's coordinates as a partner while it is being integrated, so the new
+// coordinates go to a SECOND buffer (I.crd_out); the next ED pass reads them from there.
+__global__ void __launch_bounds__(kThreads, 4) nb_finish_kernel(AccArgs A, IntArgs I) {
+    __shared__ AccSmem sm;
+    __shared__ double red[1][kWarps];
+    const int t = A.t0 + blockIdx.x;
+    double f[3];
+    nb_accumulate_tetrad(A, t, sm, f);
+    integrate_tetrad(I, t, f, red);
 }
 
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
@@ -382,6 +408,20 @@ cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int
     AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
               cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, use_hits};
     nb_accumulate_kernel<<<count, kThreads, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
+                             const unsigned char* hit, const long long* adj_off, const int* adj_partner,
+                             const int* adj_pair, double* fnb, double* e_nb, const ParamSets& ps, double* vel,
+                             double* crd_out, const double* fed, const double* rnd, double* temp, int t0, int count,
+                             int S, const SimParams& sp, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
+    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
+              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1};
+    IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
+    nb_finish_kernel<<<count, kThreads, 0, st>>>(A, I);
     return cudaGetLastError();
 }
 

@@ -83,9 +83,12 @@ class EngineBackend:
         return self.torch.as_tensor(_CudaView(ptr, nbytes, typestr, itemsize), device=self.device).view(dtype)
 
     def crd_tensor(self):
-        if self._crd is None:
-            self._crd = self._wrap(self.e.BUF_CRD, "<f8", 8, self.torch.float64)
-        return self._crd
+        # edmd_device_buffer also makes the primary coordinate buffer current (the fused finish
+        # kernel leaves new coordinates in a second buffer), so call it every time
+        ptr, nbytes = self.e.device_buffer(self.e.BUF_CRD)
+        if self._crd is None or self._crd[0] != ptr:
+            self._crd = (ptr, self._wrap(self.e.BUF_CRD, "<f8", 8, self.torch.float64))
+        return self._crd[1]
 
     def vel_tensor(self):
         if self._vel is None:
@@ -115,6 +118,7 @@ class EngineBackend:
     def nb_scan(self): self.e.nb_scan()
     def nb_accumulate(self): self.e.nb_accumulate()
     def integrate(self): self.e.integrate()
+    def nb_finish(self): self.e.nb_finish()
     def merge(self): self.e.merge()
     def build_pairlist(self): return self.e.build_pairlist()
     def sync(self): self.e.sync()
@@ -188,8 +192,11 @@ class ShardedEngine:
                 self.gather_coordinates()
                 self.b.nb_scan()
                 self.gather_hits()
-                self.b.nb_accumulate()
-                self.b.integrate()
+                if hasattr(self.b, "nb_finish"):
+                    self.b.nb_finish()          # accumulate + clip + integrate in one kernel
+                else:
+                    self.b.nb_accumulate()
+                    self.b.integrate()
 
     def merge(self):
         """4-fold overlap average needs neighbours' copies: gather state, merge everywhere."""

@@ -90,6 +90,7 @@ def load_library():
         "edmd_nb_accumulate": (C.c_int, [E]),
         "edmd_update_velocities": (C.c_int, [E]),
         "edmd_update_coordinates": (C.c_int, [E]),
+        "edmd_nb_finish": (C.c_int, [E]),
         "edmd_integrate": (C.c_int, [E]),
         "edmd_merge": (C.c_int, [E]),
         "edmd_get_energies": (C.c_int, [E, PD]),
@@ -103,6 +104,8 @@ def load_library():
         "edmd_stream": (C.c_void_p, [E]),
         "edmd_timer_start": (C.c_int, [E]),
         "edmd_timer_stop": (C.c_int, [E, PD]),
+        "edmd_mark": (C.c_int, [E, C.c_int]),
+        "edmd_mark_elapsed": (C.c_int, [E, C.c_int, C.c_int, PD]),
         "edmd_timing_enable": (C.c_int, [E, C.c_int]),
         "edmd_timing_get": (C.c_int, [E, C.c_int, PD, C.POINTER(LL)]),
         "edmd_timing_reset": (C.c_int, [E]),
@@ -346,6 +349,9 @@ class Engine:
     def update_coordinates(self):
         self._ck(self.lib.edmd_update_coordinates(self.h))
 
+    def nb_finish(self):
+        self._ck(self.lib.edmd_nb_finish(self.h))
+
     def integrate(self):
         self._ck(self.lib.edmd_integrate(self.h))
 
@@ -386,6 +392,14 @@ class Engine:
     def timer_stop(self) -> float:
         ms = C.c_double()
         self._ck(self.lib.edmd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def mark(self, slot: int):
+        self._ck(self.lib.edmd_mark(self.h, slot))
+
+    def mark_elapsed(self, a: int, b: int) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.edmd_mark_elapsed(self.h, a, b, C.byref(ms)))
         return ms.value
 
     def timing(self, on=True):
