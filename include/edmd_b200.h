@@ -76,6 +76,10 @@ int  edmd_set_params(edmd_engine* e, const edmd_params* p);
  * that electrostatics can be switched on (qfac = 332.064/4 per the comment at :240). */
 int  edmd_set_nb_consts(edmd_engine* e, double krep, double qfac);
 
+/* The clip of summed NB force components to [-1,1] belongs to Master::process_NB_Forces
+ * (master.cpp:304-305), not to EDMD::calculate_NB_Forces; on by default, switched off by the
+ * class-EDMD shim to return raw pair forces. */
+int  edmd_set_nb_clip(edmd_engine* e, int on);
 /* Arithmetic form of the NB distance pass (nb_scan_kernel): 0 = direct differences exactly
  * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (default; 4 instead of
  * 6 FP64 instructions per atom pair).  The pass only selects tetrad pairs for the exact

@@ -108,6 +108,7 @@ struct edmd_engine {
     long calls = 0;
 
     int scan_mode = 1;   // 0 direct, 1 gram (see nb.cu)
+    int nb_clip = 1;     // clip summed NB force components to [-1,1] (master.cpp:304-305)
     cudaEvent_t span0 = nullptr, span1 = nullptr;   // edmd_timer_start/stop
     std::vector<cudaEvent_t> marks;                 // edmd_mark / edmd_mark_elapsed
     bool timing = false;
@@ -263,13 +264,19 @@ int do_accumulate(edmd_engine* e, int use_hits) {
     timer_begin(e, T_ACC);
     CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off,
                             e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
-                            e->sp, use_hits, e->st));
+                            e->sp, use_hits, e->nb_clip, e->st));
     timer_end(e, T_ACC, 1);
     return 0;
 }
 // accumulate + clip + velocity + coordinate update in one kernel (edmd_step, edmd_nb_finish)
+int do_accumulate(edmd_engine* e, int use_hits);
+int do_integrate(edmd_engine* e, int do_vel, int do_crd);
 int do_finish(edmd_engine* e) {
     if (int rc = normalize(e)) return rc;
+    if (!e->nb_clip) {   // unclipped forces requested: run the two unfused kernels
+        if (int rc = do_accumulate(e, 1)) return rc;
+        return do_integrate(e, 1, 1);
+    }
     timer_begin(e, T_ACC);
     CK(launch_nb_finish(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off, e->d_adj_partner,
                         e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
@@ -376,6 +383,12 @@ int edmd_set_nb_consts(edmd_engine* e, double krep, double qfac) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->sp.krep = krep; e->sp.qfac = qfac;
     e->hits_valid = false;
+    return 0;
+}
+
+int edmd_set_nb_clip(edmd_engine* e, int on) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->nb_clip = on ? 1 : 0;
     return 0;
 }
 

@@ -23,7 +23,7 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,
                                  const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
-                                 const SimParams& sp, int use_hits, cudaStream_t st);
+                                 const SimParams& sp, int use_hits, int clip, cudaStream_t st);
 
 cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
                              const unsigned char* hit, const long long* adj_off, const int* adj_partner,

@@ -277,6 +277,7 @@ struct AccArgs {
     double cut2_eff;           // see file header
     double krep, qfac;
     int use_hits;              // 0: treat every pair as flagged
+    int clip;                  // 1: clamp force components to [-1,1] (master.cpp:304-305)
 };
 
 struct AccSmem {
@@ -366,9 +367,12 @@ __device__ __forceinline__ void nb_accumulate_tetrad(const AccArgs& A, int t, Ac
 
     // clip (master.cpp:304-305) and store; energies are sums over this tetrad's atoms
     double* F = A.fnb + (size_t)t * 3 * S;
-    f[0] = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
-    f[1] = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
-    f[2] = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
+    f[0] = F0; f[1] = F1; f[2] = F2;
+    if (A.clip) {
+        f[0] = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
+        f[1] = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
+        f[2] = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
+    }
     if (on) {
         F[tid] = f[0]; F[S + tid] = f[1]; F[2 * S + tid] = f[2];
     } else if (tid < S) {
@@ -402,11 +406,11 @@ __global__ void __launch_bounds__(kThreads, 4) nb_finish_kernel(AccArgs A, IntAr
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,
                                  const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
-                                 const SimParams& sp, int use_hits, cudaStream_t st) {
+                                 const SimParams& sp, int use_hits, int clip, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
     AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
-              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, use_hits};
+              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, use_hits, clip};
     nb_accumulate_kernel<<<count, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }
@@ -419,7 +423,7 @@ cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int*
     if (count <= 0) return cudaSuccess;
     const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
     AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
-              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1};
+              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1, 1};
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
     nb_finish_kernel<<<count, kThreads, 0, st>>>(A, I);
     return cudaGetLastError();

@@ -70,6 +70,7 @@ def load_library():
         "edmd_destroy": (None, [E]),
         "edmd_set_params": (C.c_int, [E, C.POINTER(Params)]),
         "edmd_set_nb_consts": (C.c_int, [E, C.c_double, C.c_double]),
+        "edmd_set_nb_clip": (C.c_int, [E, C.c_int]),
         "edmd_set_nb_scan_mode": (C.c_int, [E, C.c_int]),
         "edmd_upload_tetrads": (C.c_int, [E, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
         "edmd_set_state": (C.c_int, [E, C.c_void_p, C.c_int]),
