@@ -11,6 +11,11 @@ only its shard:
   * the flat tetrad-pair list is split into contiguous equal slices for the FP64 distance pass
     (the reference's NB_Index split, master.cpp:225-239).
 
+Small systems (n <= REPLICATE_MAX_TETRADS) skip the first exchange: the per-tetrad kernels cost
+~50 ns per tetrad while an all-gather costs ~50 us of latency, so every rank runs ED / accumulate /
+integrate for ALL tetrads (identical, deterministic results on every rank) and only the pair
+scan is sharded — one all-gather of hit bytes per step.
+
 Per step the path has two real exchange points, both all-gathers over NCCL/NVLink issued on
 the engine's own CUDA stream:
     ED (owned) -> all-gather post-shake coordinates (replaces MPI_Bcast(MPI_Crds), master.cpp:279)
@@ -124,11 +129,18 @@ class EngineBackend:
     def sync(self): self.e.sync()
 
 
+# Below this size the per-tetrad kernels are replicated on every rank instead of exchanging
+# coordinates (cost model in the module docstring: ~47 ns of ED+finish per tetrad vs ~50 us + 18 ns per
+# tetrad for the all-gather -> break-even near 2,000 tetrads).
+REPLICATE_MAX_TETRADS = 2048
+
+
 class ShardedEngine:
     """Runs the reference step protocol (simulation.cpp:34-55) over world_size ranks."""
 
-    def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None):
+    def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None, replicate=None):
         self.b, self.dist, self.n, self.rank, self.world, self.group = backend, dist, n_tetrads, rank, world, group
+        self.replicate = (n_tetrads <= REPLICATE_MAX_TETRADS) if replicate is None else bool(replicate)
         self.plan = None
         self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
 
@@ -154,9 +166,13 @@ class ShardedEngine:
                                         group=self.group)
 
     def gather_coordinates(self):
+        if self.replicate:
+            return          # every rank integrates every tetrad: nothing to exchange
         self._all_gather_blocks(self.b.crd_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
 
     def gather_velocities(self):
+        if self.replicate:
+            return
         self._all_gather_blocks(self.b.vel_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
 
     def gather_hits(self):
@@ -174,6 +190,8 @@ class ShardedEngine:
         self.b.set_shard(0, self.n, 0, 0)
         npairs = self.b.build_pairlist()
         self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
+        if self.replicate:
+            self.plan.t0, self.plan.t1 = 0, self.n
         self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)
         if hasattr(self.b, "invalidate"):
             self.b.invalidate()

@@ -107,7 +107,7 @@ class OracleBackend:
     def sync(self): pass
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, replicate):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     pkg = importlib.import_module("msc-project_b200")
@@ -116,7 +116,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     system = pkg.make_ring(30, kind="coil", laps=2, lap_gap=9.0)
     b = OracleBackend(po, system)
-    sh = dmod.ShardedEngine(b, dist, system.n, rank, world)
+    sh = dmod.ShardedEngine(b, dist, system.n, rank, world, replicate=replicate)
     npairs = sh.build_pairlist()
     sh.step(2, 0)
     sh.merge()
@@ -129,11 +129,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_sharded_protocol_world2_equals_single_rank(edmd, po):
+@pytest.mark.parametrize("replicate", [False, True])
+def test_sharded_protocol_world2_equals_single_rank(edmd, po, replicate):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if replicate else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, replicate)) for r in range(2)]
     for p in procs:
         p.start()
     npairs, c, v, plan = q.get(timeout=600)
@@ -146,7 +147,7 @@ def test_sharded_protocol_world2_equals_single_rank(edmd, po):
     o.step(2); o.merge()
     co, vo = o.get_state()
     assert np.array_equal(c, co) and np.array_equal(v, vo)
-    assert plan == (0, 15, 0, (npairs + 1) // 2)
+    assert plan == ((0, 30) if replicate else (0, 15)) + (0, (npairs + 1) // 2)
 
 
 def test_shard_plan_covers_everything_once(edmd):

@@ -11,7 +11,8 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 for name, s in (("coil64", pkg.make_ring(64 * 10 // 10 if False else 60, kind="coil", laps=2, lap_gap=9.0)),
                 ("coil200-uneven", pkg.make_ring(200 if world != 3 else 200, kind="coil", laps=4, lap_gap=9.0))):
     g = pkg.Engine(s, device=local)
-    sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
+    sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world,
+                            replicate=(name == "coil64"))
     npairs = sh.build_pairlist()
     sh.set_rng(1000000000, 1, 0)
     sh.step(5, 1)
