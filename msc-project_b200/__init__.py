@@ -8,6 +8,6 @@ multi-GPU driver use.  Importing it never touches ``oracle/``; constructing an
 The directory name contains a hyphen, so import it with
 ``importlib.import_module("msc-project_b200")`` (see ``tests/conftest.py``).
 """
-from .system import (EdmdSystem, ParamSet, config_params, make_gc90, make_ring,  # noqa: F401
+from .system import (EdmdSystem, ParamSet, config_params, make_gc90, make_ring, make_ragged,  # noqa: F401
                      TIMEFAC, BOLTZMANN, GENERATOR_SEED)
 from .engine import Engine, EngineError, load_library, library_path, Tetrad, build_tetrads  # noqa: F401

@@ -197,3 +197,42 @@ def make_ring(n_tetrads: int, kind: str = "ring", nev: int = 12, seed: int = GEN
     return EdmdSystem(psets, (np.arange(n) % n_psets).astype(np.int32),
                       np.full(n + 3, 63, dtype=np.int32), crd.reshape(-1), np.zeros(n * 756),
                       params, f"{kind}{n}")
+
+
+def make_ragged(n_tetrads: int = 40, seed: int = GENERATOR_SEED, nevs=(3, 12, 20, 29), lap_gap: float = 9.0) -> EdmdSystem:
+    """Edge-case system: base pairs with DIFFERENT atom counts (58..64, one 64-atom base pair so a
+    tetrad can reach the 256-atom limit), every tetrad with its own parameter set, and eigenvector
+    counts below, at and above the 12-per-chunk register tile of the ED kernel.  Geometry: the
+    double coil of make_ring (real atom overlaps)."""
+    base = make_ring(n_tetrads, kind="coil", laps=2, lap_gap=lap_gap)
+    rng = np.random.default_rng(seed + 1)
+    n = n_tetrads
+    bp_atoms = rng.integers(58, 64, size=n + 3).astype(np.int32)
+    bp_atoms[5:9] = 64                      # tetrad 5 = 4 x 64 = 256 atoms (engine maximum)
+    bp_atoms[n:n + 3] = bp_atoms[0:3]       # the ring repeats its first three base pairs
+    crd_bp = base.crd.reshape(n, 4, 63, 3)
+    extra = rng.normal(scale=0.5, size=(n + 3, 1, 3))   # 64th atom: near atom 0 of the base pair
+
+    def bp_xyz(b):
+        t, q = (b, 0) if b < n else (n - 1, b - n + 1)
+        full = np.concatenate([crd_bp[t, q], crd_bp[t, q, :1] + extra[b % n] + 1.5], axis=0)
+        return full[:bp_atoms[b]]
+
+    bps = [bp_xyz(b) for b in range(n + 3)]
+    for i in range(3):
+        bps[n + i] = bps[i]
+    psets, crd = [], []
+    for t in range(n):
+        shape = np.concatenate(bps[t:t + 4], axis=0)
+        na = shape.shape[0]
+        nev = int(nevs[t % len(nevs)])
+        avg = shape.reshape(-1) + rng.normal(0.0, 0.05, 3 * na)
+        m = rng.choice([1.008, 12.01, 14.01, 16.0, 30.97], size=na)
+        abq = np.zeros(3 * na); abq[2::3] = rng.uniform(-0.8, 0.8, na)
+        q, _ = np.linalg.qr(rng.normal(size=(3 * na, nev)))
+        psets.append(ParamSet(na, nev, avg, np.repeat(m, 3), abq,
+                              np.sort(rng.uniform(0.5, 8.0, nev))[::-1].copy(), np.ascontiguousarray(q.T)))
+        crd.append(shape.reshape(-1))
+    crd = np.concatenate(crd)
+    return EdmdSystem(psets, np.arange(n, dtype=np.int32), bp_atoms, crd, np.zeros_like(crd),
+                      config_params(), f"ragged{n}")

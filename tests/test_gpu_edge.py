@@ -1,0 +1,166 @@
+"""GPU edge cases and size-independent properties.
+
+* ragged system: base pairs of 58..64 atoms (one tetrad at the 256-atom engine maximum), every tetrad
+  with its own parameter set, 3 / 12 / 20 / 29 eigenvectors (below, at and above the ED kernel's
+  12-per-chunk register tile);
+* empty pair list, single flagged pair, engine limits;
+* properties at BASELINE sizes (C1: 1,000 tetrads all-pairs; 10^4 tetrads, random on): scan flags are a
+  superset of the true hits and both arithmetic forms agree, determinism (bit-stable reruns),
+  zero NB force on the clash-free ring, merge idempotence, sampled-tetrad parity with the oracle.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def ragged(edmd):
+    return edmd.make_ragged(40)
+
+
+def test_ragged_per_function_parity(edmd, po, ragged):
+    s = ragged
+    assert s.num_atoms.max() == 256 and s.num_atoms.min() < 250
+    o = po.Oracle(s, "port"); g = edmd.Engine(s)
+    assert g.build_pairlist() == o.build_pairs()
+    assert np.array_equal(g.get_pairlist(), o.get_pairs())
+    o.forces(random_on=False); g.ed_forces(); g.nb_forces()
+    fo, fg = o.get_forces(), g.get_forces()
+    assert rel(fg["ed"], fo["ed"]) < TOL and rel(fg["ed_energy"], fo["ed_energy"]) < TOL
+    assert np.count_nonzero(fo["nb"]) > 100
+    assert rel(fg["nb"], fo["nb"]) < TOL and rel(fg["nb_energy"], fo["nb_energy"]) < TOL
+    o.update_velocities(); o.update_coordinates(); g.update_velocities(); g.update_coordinates()
+    (co, vo), (cg, vg) = o.get_state(), g.get_state()
+    assert rel(cg, co) < TOL and rel(vg, vo) < TOL
+    o.merge(); g.merge()
+    (co, vo), (cg, vg) = o.get_state(), g.get_state()
+    assert rel(cg, co) < TOL and rel(vg, vo) < TOL
+
+
+def test_ragged_stochastic_trajectory(edmd, po, ragged):
+    s = ragged
+    o = po.Oracle(s, "port"); o.set_time(77); o.set_rng_calls(5); o.build_pairs()
+    g = edmd.Engine(s); g.build_pairlist(); g.set_rng(77, 1, 5)
+    o.step(6, random_on=True); g.step(6, random_mode=1)
+    assert np.array_equal(g.get_forces()["rnd"], o.get_forces()["rnd"])
+    (co, vo), (cg, vg) = o.get_state(), g.get_state()
+    assert rel(cg, co) < TOL and rel(vg, vo) < TOL
+
+
+def test_both_scan_modes_give_identical_results(edmd, ragged):
+    out = []
+    for mode in (0, 1):
+        g = edmd.Engine(ragged); g.set_nb_scan_mode(mode); g.build_pairlist(); g.step(4)
+        out.append(g.get_state() + (g.flagged_pairs(),))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert out[1][2] >= 1
+
+
+def test_empty_and_tiny_pair_lists(edmd, po, ragged):
+    s = ragged
+    g = edmd.Engine(s); g.set_pairlist(np.zeros((0, 2), dtype=np.int32))
+    g.step(2)
+    o = po.Oracle(s, "port"); o.set_pairs(np.zeros((0, 2), dtype=np.int32)); o.step(2)
+    assert rel(g.get_state()[0], o.get_state()[0]) < TOL
+    assert not np.any(g.get_forces()["nb"])
+    one = np.array([[9, 3]], dtype=np.int32)            # a single pair, "odd" orientation
+    g.set_pairlist(one); o.set_pairs(one)
+    g.ed_forces(); g.nb_forces(); o.forces()
+    assert rel(g.get_forces()["nb"], o.get_forces()["nb"]) < TOL or not np.any(o.get_forces()["nb"])
+
+
+def test_engine_limits_are_reported(edmd):
+    s = edmd.make_ring(20)
+    big = edmd.ParamSet(300, 2, np.zeros(900), np.ones(900), np.zeros(900), np.ones(2), np.zeros((2, 900)))
+    s2 = edmd.EdmdSystem([big], np.zeros(4, dtype=np.int32), None, np.zeros(4 * 900), np.zeros(4 * 900))
+    with pytest.raises(edmd.EngineError, match="limit"):
+        edmd.Engine(s2)
+    g = edmd.Engine(s)
+    with pytest.raises(edmd.EngineError, match="pair list"):
+        g.step(1)                                       # no pair list yet
+    with pytest.raises(edmd.EngineError):
+        g.set_pairlist(np.array([[0, 99]], dtype=np.int32))
+
+
+def test_bit_stable_reruns(edmd):
+    s = edmd.make_ring(200, kind="coil", laps=4, lap_gap=9.0)
+    res = []
+    for _ in range(3):
+        g = edmd.Engine(s); g.build_pairlist(); g.set_rng(1, 1, 0); g.step(8, random_mode=1); g.merge()
+        res.append(g.get_state())
+    for c, v in res[1:]:
+        assert np.array_equal(c, res[0][0]) and np.array_equal(v, res[0][1])
+
+
+def test_c1_full_size_properties(edmd, po):
+    """BASELINE configs[1]: 1,000 tetrads, all pairs (494,500), random off."""
+    s = edmd.make_ring(1000, kind="ring", mole_cutoff=1e9)
+    g = edmd.Engine(s)
+    assert g.build_pairlist() == 494500
+    p = g.get_pairlist()
+    sep = np.abs(p[:, 0] - p[:, 1])
+    assert sep.min() == 6 and sep.max() == 994                      # master.cpp:194-195
+    g.step(3)
+    f = g.get_forces()
+    assert not np.any(f["nb"]) and not np.any(f["nb_energy"])      # clash-free ring: exactly zero
+    assert g.flagged_pairs() == 0
+    # sampled tetrads against the oracle: the ED / integrate path of those tetrads does not depend on
+    # the others when NB forces vanish
+    pick = [0, 1, 499, 998, 999]
+    sub = s.subset(pick)
+    o = po.Oracle(sub, "port"); o.set_pairs(np.zeros((0, 2), dtype=np.int32)); o.step(3)
+    co, vo = o.get_state(); cg, vg = g.get_state()
+    off = s.off3
+    idx = np.concatenate([np.arange(off[t], off[t + 1]) for t in pick])
+    assert rel(cg[idx], co) < TOL and rel(vg[idx], vo) < TOL
+    # merge: idempotent at full size
+    g.merge(); c1, v1 = g.get_state(); g.merge(); c2, v2 = g.get_state()
+    assert rel(c2, c1) < 1e-15 and rel(v2, v1) < 1e-14
+
+
+def test_c2_size_coil_random_on(edmd, po):
+    """10^4-tetrad coil, Langevin random forces on: hit flags vs exact evaluation on a pair sample,
+    stochastic stream parity on sampled tetrads."""
+    s = edmd.make_ring(10000, kind="coil", laps=50, lap_gap=9.0)
+    g = edmd.Engine(s)
+    npairs = g.build_pairlist()
+    assert npairs > 40000
+    g.ed_forces(); g.random_terms(mode=1, time0=5, rank=1, calls_before=0); g.nb_forces()
+    crd, _ = g.get_state()
+    f = g.get_forces()
+    pairs = g.get_pairlist()
+    flagged = g.flagged_pairs()
+    assert 0 < flagged < npairs
+    # exact check of a sample of pairs with the oracle: force on tetrad t from its listed partners
+    o = po.Oracle(s.subset([0]), "port")                 # only for its libc-exact RNG below
+    picks = [0, 17, 5003, 9999]
+    for t in picks:
+        sub_ids = sorted(set([t] + [int(b if a == t else a) for a, b in pairs[(pairs[:, 0] == t) | (pairs[:, 1] == t)]]))
+        sub = s.subset(sub_ids)
+        remap = {u: i for i, u in enumerate(sub_ids)}
+        off = s.off3
+        sub.crd[:] = np.concatenate([crd[off[u]:off[u + 1]] for u in sub_ids])
+        oo = po.Oracle(sub, "port")
+        mine = pairs[(pairs[:, 0] == t) | (pairs[:, 1] == t)]
+        acc = np.zeros(756)
+        for a, b in mine:                                  # pair-list order, worker.cpp:166-179
+            oo.nb_forces_pair(remap[int(a)], remap[int(b)])
+            ff = oo.get_forces()["nb"]
+            k = remap[t]
+            acc += ff[756 * k:756 * (k + 1)]
+        assert np.array_equal(f["nb"][off[t]:off[t + 1]], np.clip(acc, -1, 1))
+    # random terms of tetrad t = call number t of the stream
+    for t in picks:
+        o.set_time(5); o.set_rng_calls(t)
+        o.random_terms(0, rank=1)
+        # masses differ per parameter set: compare the normal deviates (rnd / noise)
+        ps_o = s.psets[int(s.param_id[0])]; ps_t = s.psets[int(s.param_id[t])]
+        z_o = o.get_forces()["rnd"] / np.sqrt(ps_o.masses3)
+        z_g = f["rnd"][s.off3[t]:s.off3[t + 1]] / np.sqrt(ps_t.masses3)
+        assert np.allclose(z_g, z_o, rtol=1e-14)
