@@ -133,8 +133,16 @@ __device__ __forceinline__ double seq_sum(const double (*buf)[kSupRow], int k, i
     double s = 0.0;
     if (k < nsum) {
         const double* row = buf[k];
-#pragma unroll 4
-        for (int i = 0; i < na; i++) s = s + row[i];
+        int i = 0;
+        // 8 independent shared-memory loads in flight, then the 8 dependent adds: the chain runs at
+        // DADD latency instead of LDS + DADD latency per element
+        for (; i + 8 <= na; i += 8) {
+            const double v0 = row[i], v1 = row[i + 1], v2 = row[i + 2], v3 = row[i + 3];
+            const double v4 = row[i + 4], v5 = row[i + 5], v6 = row[i + 6], v7 = row[i + 7];
+            s = s + v0; s = s + v1; s = s + v2; s = s + v3;
+            s = s + v4; s = s + v5; s = s + v6; s = s + v7;
+        }
+        for (; i < na; i++) s = s + row[i];
     }
     return s;
 }
@@ -222,6 +230,52 @@ __global__ void __launch_bounds__(kSupThreads) superpose_kernel(SupArgs A) {
     }
 }
 
+// Sum 12 per-lane values over the warp with a halving butterfly: at each of the 5 stages a lane
+// keeps half of its values and hands the other half to its partner, so the 12 sums cost
+// 6+3+2+1+1 = 13 adds and exchanges per lane instead of 12 x 5.  On return lane l holds the warp
+// total of value index reduce12_index(l) (or garbage where that is -1).  Fixed order -> bit-stable.
+__device__ __forceinline__ int reduce12_index(int lane) {
+    const int b4 = (lane >> 4) & 1, b3 = (lane >> 3) & 1, b2 = (lane >> 2) & 1, b1 = (lane >> 1) & 1;
+    if (b2 && b1) return -1;
+    return 6 * b4 + 3 * b3 + (b2 ? 2 : b1);
+}
+__device__ __forceinline__ double warp_reduce12(const double (&v)[12], int lane) {
+    const unsigned full = 0xffffffffu;
+    double a[6];
+    {   // stage 16: 12 -> 6
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double keep = hi ? v[i + 6] : v[i], send = hi ? v[i] : v[i + 6];
+            a[i] = keep + __shfl_xor_sync(full, send, 16);
+        }
+    }
+    double b[3];
+    {   // stage 8: 6 -> 3
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const double keep = hi ? a[i + 3] : a[i], send = hi ? a[i] : a[i + 3];
+            b[i] = keep + __shfl_xor_sync(full, send, 8);
+        }
+    }
+    double c[2];
+    {   // stage 4: 3 -> 2 (value 3 is padding)
+        const bool hi = lane & 4;
+        const double k0 = hi ? b[2] : b[0], s0 = hi ? b[0] : b[2];
+        const double k1 = hi ? 0.0 : b[1], s1 = hi ? b[1] : 0.0;
+        c[0] = k0 + __shfl_xor_sync(full, s0, 4);
+        c[1] = k1 + __shfl_xor_sync(full, s1, 4);
+    }
+    double d;
+    {   // stage 2: 2 -> 1
+        const bool hi = lane & 2;
+        const double keep = hi ? c[1] : c[0], send = hi ? c[0] : c[1];
+        d = keep + __shfl_xor_sync(full, send, 2);
+    }
+    return d + __shfl_xor_sync(full, d, 1);   // stage 1
+}
+
 struct EdArgs {
     ParamSets ps;
     const int* param_id;
@@ -232,6 +286,9 @@ struct EdArgs {
     const double* sup;   // [n][kSupWords] from superpose_kernel
     int t0;              // first tetrad of this launch
     double scaled;
+    const int* order;    // [count] tetrads of this launch sorted by parameter set
+    int count;
+    int chunk;           // tetrads per CTA
 };
 
 __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
@@ -239,121 +296,160 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
     __shared__ double sProj[64];
     __shared__ double sPw[64];
 
-    const int t = A.t0 + blockIdx.x;
     const int tid = threadIdx.x;
-    const int ps = A.param_id[t];
-    const int na = A.ps.na[ps], nev = A.ps.nev[ps];
     const int S = A.ps.S;
-    const bool on = tid < na;
-    double* X = A.crd + (size_t)t * 3 * S;
-    const double* XIN = A.crd_in + (size_t)t * 3 * S;
-    const double* AV = A.ps.avg + (size_t)ps * 3 * S;
-    const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
-    const double* EL = A.ps.eval + (size_t)ps * A.ps.NEV;
-    const double* SUP = A.sup + (size_t)t * kSupWords;
+    const int e0 = blockIdx.x * A.chunk;
+    const int e1 = (e0 + A.chunk < A.count) ? e0 + A.chunk : A.count;
 
-    double x0 = 0, x1 = 0, x2 = 0, a0 = 0, a1 = 0, a2 = 0;
-    if (on) {
-        x0 = XIN[tid]; x1 = XIN[S + tid]; x2 = XIN[2 * S + tid];
-        a0 = AV[tid]; a1 = AV[S + tid]; a2 = AV[2 * S + tid];
-    }
+    // A CTA walks a run of tetrads that (mostly) share one parameter set: the thread's 3 x 12
+    // eigenvector coefficients and its atom of the average structure stay in registers across the
+    // run, so a shared parameter table is read once per run instead of once per tetrad.
+    int cur_ps = -1, na = 0, nev = 0;
+    bool on = false;
+    double a0 = 0, a1 = 0, a2 = 0;
     double ev[kNevReg][3];
-    const int nchunk0 = nev < kNevReg ? nev : kNevReg;
-#pragma unroll
-    for (int j = 0; j < kNevReg; j++) {
-        ev[j][0] = ev[j][1] = ev[j][2] = 0.0;
-        if (on && j < nchunk0) {
-            const double* e = EV + (size_t)j * 3 * S;
-            ev[j][0] = e[tid]; ev[j][1] = e[S + tid]; ev[j][2] = e[2 * S + tid];
-        }
-    }
-    double R[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = SUP[k];
-    const double shift0 = SUP[9], shift1 = SUP[10], shift2 = SUP[11];
+    const double* EV = nullptr;
+    const double* EL = nullptr;
 
-    // displacement in the reference frame, edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
-    double d0 = 0, d1 = 0, d2 = 0;
-    if (on) {
-        const double ac0 = a0 - SUP[12], ac1 = a1 - SUP[13], ac2 = a2 - SUP[14];
-        const double xc0 = x0 - SUP[15], xc1 = x1 - SUP[16], xc2 = x2 - SUP[17];
-        d0 = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
-        d1 = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
-        d2 = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
-    }
-
-    // projections (edmd.cpp:106-110), kNevReg eigenvectors per pass
-    for (int j0 = 0; j0 < nev; j0 += kNevReg) {
-        if (j0 > 0) {
+    for (int e = e0; e < e1; e++) {
+        const int t = A.order[e];
+        const int ps = A.param_id[t];
+        if (ps != cur_ps) {
+            cur_ps = ps;
+            na = A.ps.na[ps]; nev = A.ps.nev[ps];
+            on = tid < na;
+            const double* AV = A.ps.avg + (size_t)ps * 3 * S;
+            EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
+            EL = A.ps.eval + (size_t)ps * A.ps.NEV;
+            a0 = a1 = a2 = 0.0;
+            if (on) { a0 = AV[tid]; a1 = AV[S + tid]; a2 = AV[2 * S + tid]; }
+            const int nchunk0 = nev < kNevReg ? nev : kNevReg;
 #pragma unroll
             for (int j = 0; j < kNevReg; j++) {
                 ev[j][0] = ev[j][1] = ev[j][2] = 0.0;
-                if (on && j0 + j < nev) {
-                    const double* e = EV + (size_t)(j0 + j) * 3 * S;
-                    ev[j][0] = e[tid]; ev[j][1] = e[S + tid]; ev[j][2] = e[2 * S + tid];
+                if (on && j < nchunk0) {
+                    const double* c = EV + (size_t)j * 3 * S;
+                    ev[j][0] = c[tid]; ev[j][1] = c[S + tid]; ev[j][2] = c[2 * S + tid];
                 }
             }
-        }
-        double v[kNevReg];
-#pragma unroll
-        for (int j = 0; j < kNevReg; j++) v[j] = ev[j][0] * d0 + ev[j][1] * d1 + ev[j][2] * d2;
-        block_sum<kNevReg>(v, red);
-        if (tid < kNevReg && j0 + tid < nev) {
-            sProj[j0 + tid] = v[tid];
-            sPw[j0 + tid] = v[tid] * A.scaled / EL[j0 + tid];
-        }
-    }
-    __syncthreads();
-
-    // re-embedding and force in the reference frame (edmd.cpp:113-127)
-    double s0 = a0, s1 = a1, s2 = a2, f0 = 0, f1 = 0, f2 = 0;
-    for (int j0 = 0; j0 < nev; j0 += kNevReg) {
-        if (nev > kNevReg) {   // multi-chunk: stream the coefficients again (L2-resident)
+        } else if (nev > kNevReg) {   // multi-chunk sets end a tetrad with the LAST chunk in registers
 #pragma unroll
             for (int j = 0; j < kNevReg; j++) {
                 ev[j][0] = ev[j][1] = ev[j][2] = 0.0;
-                if (on && j0 + j < nev) {
-                    const double* e = EV + (size_t)(j0 + j) * 3 * S;
-                    ev[j][0] = e[tid]; ev[j][1] = e[S + tid]; ev[j][2] = e[2 * S + tid];
+                if (on) {
+                    const double* c = EV + (size_t)j * 3 * S;
+                    ev[j][0] = c[tid]; ev[j][1] = c[S + tid]; ev[j][2] = c[2 * S + tid];
                 }
             }
         }
+        double* X = A.crd + (size_t)t * 3 * S;
+        const double* XIN = A.crd_in + (size_t)t * 3 * S;
+        const double* SUP = A.sup + (size_t)t * kSupWords;
+
+        double x0 = 0, x1 = 0, x2 = 0;
+        if (on) { x0 = XIN[tid]; x1 = XIN[S + tid]; x2 = XIN[2 * S + tid]; }
+        double R[9];
 #pragma unroll
-        for (int j = 0; j < kNevReg; j++) {
-            if (j0 + j < nev) {
-                const double p = sProj[j0 + j], w = sPw[j0 + j];
-                s0 += ev[j][0] * p; s1 += ev[j][1] * p; s2 += ev[j][2] * p;
-                f0 -= ev[j][0] * w; f1 -= ev[j][1] * w; f2 -= ev[j][2] * w;
+        for (int k = 0; k < 9; k++) R[k] = SUP[k];
+        const double shift0 = SUP[9], shift1 = SUP[10], shift2 = SUP[11];
+
+        // displacement in the reference frame, edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
+        double d0 = 0, d1 = 0, d2 = 0;
+        if (on) {
+            const double ac0 = a0 - SUP[12], ac1 = a1 - SUP[13], ac2 = a2 - SUP[14];
+            const double xc0 = x0 - SUP[15], xc1 = x1 - SUP[16], xc2 = x2 - SUP[17];
+            d0 = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
+            d1 = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
+            d2 = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
+        }
+
+        // projections (edmd.cpp:106-110), kNevReg eigenvectors per pass
+        for (int j0 = 0; j0 < nev; j0 += kNevReg) {
+            if (j0 > 0) {
+#pragma unroll
+                for (int j = 0; j < kNevReg; j++) {
+                    ev[j][0] = ev[j][1] = ev[j][2] = 0.0;
+                    if (on && j0 + j < nev) {
+                        const double* c = EV + (size_t)(j0 + j) * 3 * S;
+                        ev[j][0] = c[tid]; ev[j][1] = c[S + tid]; ev[j][2] = c[2 * S + tid];
+                    }
+                }
+            }
+            double v[kNevReg];
+#pragma unroll
+            for (int j = 0; j < kNevReg; j++) v[j] = fma(ev[j][0], d0, fma(ev[j][1], d1, ev[j][2] * d2));
+            {   // CTA sum of the 12 partial projections: warp butterfly, then 12 threads add the 8 warps
+                const int lane = tid & 31, warp = tid >> 5;
+                const double w = warp_reduce12(v, lane);
+                const int idx = reduce12_index(lane);
+                if (idx >= 0 && !(lane & 1)) red[idx][warp] = w;
+                __syncthreads();
+                if (tid < kNevReg && j0 + tid < nev) {
+                    double p = red[tid][0];
+#pragma unroll
+                    for (int q = 1; q < kWarps; q++) p += red[tid][q];
+                    sProj[j0 + tid] = p;
+                    sPw[j0 + tid] = p * A.scaled / EL[j0 + tid];
+                }
+                if (j0 + kNevReg < nev) __syncthreads();   // red[] is reused by the next chunk
             }
         }
-    }
-    // back to the laboratory frame (edmd.cpp:130-150): x = R^T (s - shift), F = R^T f
-    if (on) {
-        s0 -= shift0; s1 -= shift1; s2 -= shift2;
-        X[tid]         = R[0] * s0 + R[3] * s1 + R[6] * s2;
-        X[S + tid]     = R[1] * s0 + R[4] * s1 + R[7] * s2;
-        X[2 * S + tid] = R[2] * s0 + R[5] * s1 + R[8] * s2;
-        double* F = A.fed + (size_t)t * 3 * S;
-        F[tid]         = R[0] * f0 + R[3] * f1 + R[6] * f2;
-        F[S + tid]     = R[1] * f0 + R[4] * f1 + R[7] * f2;
-        F[2 * S + tid] = R[2] * f0 + R[5] * f1 + R[8] * f2;
-    }
-    if (tid == 0) {   // edmd.cpp:153-157
-        double e = 0.0;
-        for (int j = 0; j < nev; j++) e += sProj[j] * sProj[j] / EL[j];
-        A.e_ed[t] = e * (0.5 * A.scaled);
+        __syncthreads();
+
+        // re-embedding and force in the reference frame (edmd.cpp:113-127)
+        double s0 = a0, s1 = a1, s2 = a2, f0 = 0, f1 = 0, f2 = 0;
+        for (int j0 = 0; j0 < nev; j0 += kNevReg) {
+            if (nev > kNevReg) {   // multi-chunk: stream the coefficients again (L2-resident)
+#pragma unroll
+                for (int j = 0; j < kNevReg; j++) {
+                    ev[j][0] = ev[j][1] = ev[j][2] = 0.0;
+                    if (on && j0 + j < nev) {
+                        const double* c = EV + (size_t)(j0 + j) * 3 * S;
+                        ev[j][0] = c[tid]; ev[j][1] = c[S + tid]; ev[j][2] = c[2 * S + tid];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kNevReg; j++) {
+                if (j0 + j < nev) {
+                    const double p = sProj[j0 + j], w = sPw[j0 + j];
+                    s0 = fma(ev[j][0], p, s0); s1 = fma(ev[j][1], p, s1); s2 = fma(ev[j][2], p, s2);
+                    f0 = fma(-ev[j][0], w, f0); f1 = fma(-ev[j][1], w, f1); f2 = fma(-ev[j][2], w, f2);
+                }
+            }
+        }
+        // back to the laboratory frame (edmd.cpp:130-150): x = R^T (s - shift), F = R^T f
+        if (on) {
+            s0 -= shift0; s1 -= shift1; s2 -= shift2;
+            X[tid]         = R[0] * s0 + R[3] * s1 + R[6] * s2;
+            X[S + tid]     = R[1] * s0 + R[4] * s1 + R[7] * s2;
+            X[2 * S + tid] = R[2] * s0 + R[5] * s1 + R[8] * s2;
+            double* F = A.fed + (size_t)t * 3 * S;
+            F[tid]         = R[0] * f0 + R[3] * f1 + R[6] * f2;
+            F[S + tid]     = R[1] * f0 + R[4] * f1 + R[7] * f2;
+            F[2 * S + tid] = R[2] * f0 + R[5] * f1 + R[8] * f2;
+        }
+        if (tid == 0) {   // edmd.cpp:153-157
+            double en = 0.0;
+            for (int j = 0; j < nev; j++) en += sProj[j] * sProj[j] / EL[j];
+            A.e_ed[t] = en * (0.5 * A.scaled);
+        }
     }
 }
 
 cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
-                             double* e_ed, double* sup, int t0, int count, double scaled, cudaStream_t st) {
+                             double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
+                             cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0};
     superpose_kernel<<<count, kSupThreads, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled};
-    ed_project_kernel<<<count, kThreads, 0, st>>>(A);
+    int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8) chunk = 8;
+    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
+    ed_project_kernel<<<(count + chunk - 1) / chunk, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }
 

@@ -68,6 +68,7 @@ struct edmd_engine {
 
     // device: metadata + parameter sets
     int *d_natoms = nullptr, *d_param_id = nullptr, *d_ps_na = nullptr, *d_ps_nev = nullptr;
+    int* d_order = nullptr;   // owned tetrads [t0,t1) sorted by parameter set (ED project kernel)
     long long* d_off3 = nullptr;
     double *d_avg = nullptr, *d_mass = nullptr, *d_chg = nullptr, *d_eval = nullptr, *d_evec = nullptr;
     ParamSets ps{};
@@ -146,6 +147,7 @@ void timer_fold(edmd_engine* e, int id) {
 }
 
 void free_system(edmd_engine* e) {
+    cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_natoms); cudaFree(e->d_param_id); cudaFree(e->d_ps_na); cudaFree(e->d_ps_nev);
     cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
     cudaFree(e->d_eval); cudaFree(e->d_evec);
@@ -234,6 +236,19 @@ int check_ready(edmd_engine* e, bool need_pairs) {
     return 0;
 }
 
+// Owned tetrads sorted (stably) by parameter set: consecutive tetrads of a CTA's run share the
+// eigenvector registers in ed_project_kernel.
+int upload_order(edmd_engine* e) {
+    std::vector<int> ord;
+    ord.reserve(e->t1 - e->t0);
+    for (int t = e->t0; t < e->t1; t++) ord.push_back(t);
+    std::stable_sort(ord.begin(), ord.end(), [e](int a, int b) { return e->param_id_h[a] < e->param_id_h[b]; });
+    if (!e->d_order) CK(dev_alloc(&e->d_order, (size_t)e->n));
+    if (!ord.empty()) CK(cudaMemcpyAsync(e->d_order, ord.data(), sizeof(int) * ord.size(), cudaMemcpyHostToDevice, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
 // The fused finish kernel leaves the owned tetrads' new coordinates in crd2 (other CTAs may still
 // be reading crd).  The ED pass consumes them from there; every other consumer calls this first.
 int normalize(edmd_engine* e) {
@@ -248,7 +263,8 @@ int do_ed(edmd_engine* e) {
     timer_begin(e, T_ED);
     const double* src = e->latest_in_crd2 ? e->crd2 : e->crd;
     e->latest_in_crd2 = false;
-    CK(launch_ed_forces(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->t0, e->t1 - e->t0, e->sp.scaled, e->st));
+    CK(launch_ed_forces(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
+                        e->t1 - e->t0, e->sp.scaled, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -507,6 +523,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
 
     e->ps = ParamSets{e->d_ps_na, e->d_ps_nev, e->d_avg, e->d_mass, e->d_chg, e->d_eval, e->d_evec, S, NEV};
     e->t0 = 0; e->t1 = n; e->p0 = e->p1 = 0; e->shard_pairs_custom = false;
+    if (int rc = upload_order(e)) return rc;
 
     if (bp_atoms) {
         std::vector<int> off(n + 4, 0);
@@ -733,8 +750,10 @@ int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
     if (p0 < 0 || p0 > p1 || (e->have_pairs && p1 > e->np)) return fail(EDMD_ERR_ARG, "pair shard out of range");
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
+    const bool range_changed = (t0 != e->t0 || t1 != e->t1);
     e->t0 = t0; e->t1 = t1; e->p0 = p0; e->p1 = p1; e->shard_pairs_custom = true;
     e->hits_valid = false;
+    if (range_changed) return upload_order(e);
     return 0;
 }
 
