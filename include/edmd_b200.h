@@ -119,6 +119,8 @@ int edmd_get_forces_flat(edmd_engine* e, double* ed, double* ed_energy, double* 
 /* Replaces Master::cal_Centre_of_Mass + generate_Pair_Lists (master.cpp:157-210): same
  * inclusion predicate, same (t1,t2) orientation, same order; 64-bit count. */
 int edmd_build_pairlist(edmd_engine* e, long long* num_pairs);
+/* 0 = auto, 1 = the reference's O(n^2) sweep, 2 = uniform-grid cell list (same list, same order). */
+int edmd_set_pair_builder(edmd_engine* e, int which);
 int edmd_get_pairlist(edmd_engine* e, int* pairs /* 2*num_pairs */, long long cap_pairs);
 /* Install a caller-made list (tests, custom schedules). */
 int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long num_pairs);

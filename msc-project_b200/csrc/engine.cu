@@ -94,6 +94,12 @@ struct edmd_engine {
     bool have_pairs = false;
     bool hits_valid = false;
 
+    // cell-list builder scratch (pairlist.cu), grown on demand
+    unsigned long long *d_cell = nullptr, *d_cell_sorted = nullptr;
+    int *d_tet = nullptr, *d_tet_sorted = nullptr, *d_partners = nullptr, *d_partners_sorted = nullptr;
+    void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0; long long partners_cap = 0;
+    int pair_builder = 0;   // 0 auto, 1 sweep (reference O(n^2)), 2 cell list
+
     // merge
     int* d_bp_off = nullptr;
     bool have_bp = false;
@@ -148,6 +154,10 @@ void timer_fold(edmd_engine* e, int id) {
 
 void free_system(edmd_engine* e) {
     cudaFree(e->d_order); e->d_order = nullptr;
+    cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
+    cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
+    e->d_cell = e->d_cell_sorted = nullptr; e->d_tet = e->d_tet_sorted = e->d_partners = e->d_partners_sorted = nullptr;
+    e->d_cub_tmp = nullptr; e->cub_tmp_bytes = 0; e->partners_cap = 0;
     cudaFree(e->d_natoms); cudaFree(e->d_param_id); cudaFree(e->d_ps_na); cudaFree(e->d_ps_nev);
     cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
     cudaFree(e->d_eval); cudaFree(e->d_evec);
@@ -683,6 +693,12 @@ int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n) {
     return 0;
 }
 
+int edmd_set_pair_builder(edmd_engine* e, int which) {
+    if (!e || which < 0 || which > 2) return fail(EDMD_ERR_ARG, "pair builder must be 0 (auto), 1 (sweep) or 2 (cells)");
+    e->pair_builder = which;
+    return 0;
+}
+
 int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     if (int rc = check_ready(e, false)) return rc;
     CK(cudaSetDevice(e->device));
@@ -691,7 +707,39 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     const double cut2 = e->sp.mole_cutoff * e->sp.mole_cutoff;
     timer_begin(e, T_PAIRS);
     CK(launch_centroids(e->crd, e->d_natoms, e->cen, n, e->S, e->st));
-    CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, nullptr, nullptr, 0, e->st));
+
+    // builder choice: the cell list pays off when the cutoff is small against the extent
+    bool cells = false;
+    CellGridHost grid{};
+    if (e->pair_builder != 1 && e->sp.mole_cutoff > 0.0 && e->sp.mole_cutoff < 1e8) {
+        std::vector<double> cen(4 * (size_t)n);
+        CK(cudaMemcpyAsync(cen.data(), e->cen, sizeof(double) * cen.size(), cudaMemcpyDeviceToHost, e->st));
+        CK(cudaStreamSynchronize(e->st));
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        bool finite = true;
+        for (int t = 0; t < n; t++)
+            for (int c = 0; c < 3; c++) {
+                const double v = cen[4 * (size_t)t + c];
+                if (!(v > -1e15 && v < 1e15)) finite = false;
+                lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v);
+            }
+        const double h = e->sp.mole_cutoff;
+        const double ncell = finite ? (floor((hi[0] - lo[0]) / h) + 1) * (floor((hi[1] - lo[1]) / h) + 1) *
+                                          (floor((hi[2] - lo[2]) / h) + 1) : 0.0;
+        cells = finite && ncell < 9e18 && (e->pair_builder == 2 || (n >= 4096 && ncell >= 64.0));
+        if (cells) {
+            if (!e->d_cell) {
+                CK(dev_alloc(&e->d_cell, (size_t)n)); CK(dev_alloc(&e->d_cell_sorted, (size_t)n));
+                CK(dev_alloc(&e->d_tet, (size_t)n)); CK(dev_alloc(&e->d_tet_sorted, (size_t)n));
+            }
+            CK(cell_sort_tetrads(e->cen, n, lo, hi, h, &grid, e->d_cell, e->d_cell_sorted, e->d_tet, e->d_tet_sorted,
+                                 &e->d_cub_tmp, &e->cub_tmp_bytes, e->st));
+        }
+    }
+
+    if (cells) CK(launch_cell_rows(e->cen, n, cut2, e->sp.mole_least, grid, e->d_cell_sorted, e->d_tet_sorted,
+                                   e->d_row_count, nullptr, nullptr, 0, e->st));
+    else CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, nullptr, nullptr, 0, e->st));
     std::vector<long long> cnt(n), off(n + 1, 0);
     CK(cudaMemcpyAsync(cnt.data(), e->d_row_count, sizeof(long long) * n, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
@@ -700,8 +748,22 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     if (np >= (1LL << 31)) return fail(EDMD_ERR_LIMIT, "%lld pairs exceeds the 2^31 pair-index limit", np);
     if (int rc = ensure_pair_capacity(e, np)) return rc;
     CK(cudaMemcpyAsync(e->d_row_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
-    CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, e->d_row_off, e->d_pairs, 1, e->st));
-    timer_end(e, T_PAIRS, 3);
+    if (cells) {
+        if (np > e->partners_cap) {
+            cudaFree(e->d_partners); cudaFree(e->d_partners_sorted);
+            e->d_partners = e->d_partners_sorted = nullptr; e->partners_cap = 0;
+            const long long cap = np + np / 4 + 1024;
+            CK(dev_alloc(&e->d_partners, (size_t)cap)); CK(dev_alloc(&e->d_partners_sorted, (size_t)cap));
+            e->partners_cap = cap;
+        }
+        CK(launch_cell_rows(e->cen, n, cut2, e->sp.mole_least, grid, e->d_cell_sorted, e->d_tet_sorted,
+                            e->d_row_count, e->d_row_off, e->d_partners, 1, e->st));
+        CK(sort_rows_and_emit(e->d_partners, e->d_partners_sorted, e->d_row_off, n, np, e->d_pairs,
+                              &e->d_cub_tmp, &e->cub_tmp_bytes, e->st));
+    } else {
+        CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, e->d_row_off, e->d_pairs, 1, e->st));
+    }
+    timer_end(e, T_PAIRS, cells ? 6 : 3);
     std::vector<int2> pairs((size_t)np);
     if (np) CK(cudaMemcpyAsync(pairs.data(), e->d_pairs, sizeof(int2) * np, cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));

@@ -43,6 +43,17 @@ cudaError_t launch_centroids(const double* crd, const int* natoms, double* cen, 
 cudaError_t launch_pair_rows(const double* cen, int n, double cut2, double least, long long* row_count,
                              const long long* row_off, int2* pairs, int fill, cudaStream_t st);
 
+// cell-list pair builder (pairlist.cu)
+struct CellGridHost { double x0, y0, z0, inv_h; long long nx, ny, nz; };
+cudaError_t cell_sort_tetrads(const double* cen, int n, const double lo[3], const double hi[3], double h,
+                              CellGridHost* grid_out, unsigned long long* cell, unsigned long long* cell_sorted,
+                              int* tet, int* tet_sorted, void** tmp, size_t* tmp_bytes, cudaStream_t st);
+cudaError_t launch_cell_rows(const double* cen, int n, double cut2, double least, const CellGridHost& g,
+                             const unsigned long long* cell_sorted, const int* tet_sorted, long long* row_count,
+                             const long long* row_off, int* partners, int fill, cudaStream_t st);
+cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const long long* row_off, int n,
+                               long long np, int2* pairs, void** tmp, size_t* tmp_bytes, cudaStream_t st);
+
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,

@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_segmented_sort.cuh>
+
 namespace edmd {
 
 __global__ void centroid_kernel(const double* crd, const int* natoms, double* cen, int n, int S) {
@@ -60,6 +63,145 @@ __global__ void pair_rows_kernel(const double* cen, int n, double cut2, double l
         }
         if (!fill && lane == 0) row_count[i] = cnt;
     }
+}
+
+// ---- cell list ---------------------------------------------------------------------------------
+// The O(n^2) sweep above is the reference's algorithm (master.cpp:188-189); beyond ~1e5 tetrads it is
+// replaced by a uniform grid of cells of edge mole_Cutoff: tetrads are radix-sorted by cell id
+// (stable, so ascending inside a cell), a warp per row visits the 27 neighbouring cells through
+// binary searches in the sorted cell-id array (no dense cell table, any extent), and each row's
+// partners are sorted ascending afterwards — the SAME list in the SAME order as the sweep.
+struct CellGrid {
+    double x0, y0, z0, inv_h;
+    long long nx, ny, nz;
+};
+
+__device__ __forceinline__ long long cell_of(const CellGrid& G, const double* c, long long& ix, long long& iy, long long& iz) {
+    ix = (long long)floor((c[0] - G.x0) * G.inv_h);
+    iy = (long long)floor((c[1] - G.y0) * G.inv_h);
+    iz = (long long)floor((c[2] - G.z0) * G.inv_h);
+    ix = ix < 0 ? 0 : (ix >= G.nx ? G.nx - 1 : ix);
+    iy = iy < 0 ? 0 : (iy >= G.ny ? G.ny - 1 : iy);
+    iz = iz < 0 ? 0 : (iz >= G.nz ? G.nz - 1 : iz);
+    return ix + G.nx * (iy + G.ny * iz);
+}
+
+__global__ void cell_id_kernel(const double* cen, int n, CellGrid G, unsigned long long* cell, int* ident) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    long long ix, iy, iz;
+    cell[t] = (unsigned long long)cell_of(G, cen + 4 * (size_t)t, ix, iy, iz);
+    ident[t] = t;
+}
+
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long* a, int n, unsigned long long key) {
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// fill == 0: row_count[i] = number of partners j > i.  fill == 1: partners written (unordered) at
+// row_off[i].  One warp per row.
+__global__ void cell_rows_kernel(const double* cen, int n, double cut2, double least, CellGrid G,
+                                 const unsigned long long* sorted_cell, const int* sorted_tet,
+                                 long long* row_count, const long long* row_off, int* partners, int fill) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+        long long ix, iy, iz;
+        cell_of(G, cen + 4 * (size_t)i, ix, iy, iz);
+        int lo = 0, hi = 0;
+        if (lane < 27) {
+            const long long cx = ix + (lane % 3) - 1, cy = iy + ((lane / 3) % 3) - 1, cz = iz + (lane / 9) - 1;
+            if (cx >= 0 && cx < G.nx && cy >= 0 && cy < G.ny && cz >= 0 && cz < G.nz) {
+                const unsigned long long c = (unsigned long long)(cx + G.nx * (cy + G.ny * cz));
+                lo = lower_bound_u64(sorted_cell, n, c);
+                hi = lower_bound_u64(sorted_cell, n, c + 1);
+            }
+        }
+        long long cnt = 0;
+        const long long off = fill ? row_off[i] : 0;
+        for (int k = 0; k < 27; k++) {
+            const int a = __shfl_sync(0xffffffffu, lo, k), b = __shfl_sync(0xffffffffu, hi, k);
+            for (int m0 = a; m0 < b; m0 += 32) {
+                const int m = m0 + lane;
+                int j = -1;
+                bool in = false;
+                if (m < b) { j = sorted_tet[m]; in = (j > i) && pair_included(cen, i, j, n, cut2, least); }
+                const unsigned bal = __ballot_sync(0xffffffffu, in);
+                if (fill && in) partners[off + cnt + __popc(bal & ((1u << lane) - 1u))] = j;
+                cnt += __popc(bal);
+            }
+        }
+        if (!fill && lane == 0) row_count[i] = cnt;
+    }
+}
+
+// rows of sorted partners -> (t1,t2) with the orientation rule of master.cpp:197-201
+__global__ void rows_to_pairs_kernel(const int* partners, const long long* row_off, int n, int2* pairs) {
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * warps_per_block + (threadIdx.x >> 5); i < n; i += gridDim.x * warps_per_block) {
+        for (long long p = row_off[i] + lane; p < row_off[i + 1]; p += 32) {
+            const int j = partners[p];
+            pairs[p] = ((j - i) & 1) ? make_int2(j, i) : make_int2(i, j);
+        }
+    }
+}
+
+cudaError_t cell_sort_tetrads(const double* cen, int n, const double lo[3], const double hi[3], double h,
+                              CellGridHost* grid_out, unsigned long long* cell, unsigned long long* cell_sorted,
+                              int* tet, int* tet_sorted, void** tmp, size_t* tmp_bytes, cudaStream_t st) {
+    CellGrid G;
+    G.x0 = lo[0]; G.y0 = lo[1]; G.z0 = lo[2]; G.inv_h = 1.0 / h;
+    G.nx = (long long)floor((hi[0] - lo[0]) / h) + 1; G.ny = (long long)floor((hi[1] - lo[1]) / h) + 1;
+    G.nz = (long long)floor((hi[2] - lo[2]) / h) + 1;
+    grid_out->x0 = G.x0; grid_out->y0 = G.y0; grid_out->z0 = G.z0; grid_out->inv_h = G.inv_h;
+    grid_out->nx = G.nx; grid_out->ny = G.ny; grid_out->nz = G.nz;
+    cell_id_kernel<<<(n + 255) / 256, 256, 0, st>>>(cen, n, G, cell, tet);
+    size_t need = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, need, cell, cell_sorted, tet, tet_sorted, n, 0, 64, st);
+    if (need > *tmp_bytes) {
+        cudaFree(*tmp);
+        cudaError_t err = cudaMalloc(tmp, need);
+        if (err != cudaSuccess) { *tmp = nullptr; *tmp_bytes = 0; return err; }
+        *tmp_bytes = need;
+    }
+    return cub::DeviceRadixSort::SortPairs(*tmp, need, cell, cell_sorted, tet, tet_sorted, n, 0, 64, st);
+}
+
+cudaError_t launch_cell_rows(const double* cen, int n, double cut2, double least, const CellGridHost& g,
+                             const unsigned long long* cell_sorted, const int* tet_sorted, long long* row_count,
+                             const long long* row_off, int* partners, int fill, cudaStream_t st) {
+    CellGrid G{g.x0, g.y0, g.z0, g.inv_h, g.nx, g.ny, g.nz};
+    const int wpb = 8;
+    int grid = (n + wpb - 1) / wpb;
+    if (grid > 148 * 16) grid = 148 * 16;
+    cell_rows_kernel<<<grid, wpb * 32, 0, st>>>(cen, n, cut2, least, G, cell_sorted, tet_sorted, row_count, row_off,
+                                                partners, fill);
+    return cudaGetLastError();
+}
+
+cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const long long* row_off, int n,
+                               long long np, int2* pairs, void** tmp, size_t* tmp_bytes, cudaStream_t st) {
+    if (np > 0) {
+        size_t need = 0;
+        cub::DeviceSegmentedSort::SortKeys(nullptr, need, partners, partners_sorted, np, n, row_off, row_off + 1, st);
+        if (need > *tmp_bytes) {
+            cudaFree(*tmp);
+            cudaError_t err = cudaMalloc(tmp, need);
+            if (err != cudaSuccess) { *tmp = nullptr; *tmp_bytes = 0; return err; }
+            *tmp_bytes = need;
+        }
+        cudaError_t err = cub::DeviceSegmentedSort::SortKeys(*tmp, need, partners, partners_sorted, np, n, row_off,
+                                                             row_off + 1, st);
+        if (err != cudaSuccess) return err;
+    }
+    const int wpb = 8;
+    int grid = (n + wpb - 1) / wpb;
+    if (grid > 148 * 16) grid = 148 * 16;
+    rows_to_pairs_kernel<<<grid, wpb * 32, 0, st>>>(partners_sorted, row_off, n, pairs);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_centroids(const double* crd, const int* natoms, double* cen, int n, int S, cudaStream_t st) {

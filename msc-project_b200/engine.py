@@ -80,6 +80,7 @@ def load_library():
         "edmd_set_state_flat": (C.c_int, [E, PD, PD]),
         "edmd_get_state_flat": (C.c_int, [E, PD, PD]),
         "edmd_get_forces_flat": (C.c_int, [E, PD, PD, PD, PD, PD, PD]),
+        "edmd_set_pair_builder": (C.c_int, [E, C.c_int]),
         "edmd_build_pairlist": (C.c_int, [E, C.POINTER(LL)]),
         "edmd_get_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
         "edmd_set_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
@@ -299,6 +300,9 @@ class Engine:
         self._ck(self.lib.edmd_get_state_flat(self.h, _ptr(crd), _ptr(vel)))
 
     # ---- pair list --------------------------------------------------------------------
+    def set_pair_builder(self, which: int):
+        self._ck(self.lib.edmd_set_pair_builder(self.h, which))
+
     def build_pairlist(self) -> int:
         npairs = C.c_longlong()
         self._ck(self.lib.edmd_build_pairlist(self.h, C.byref(npairs)))

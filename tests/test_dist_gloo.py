@@ -61,6 +61,9 @@ class OracleBackend:
         self.hit = torch.zeros(npairs, dtype=torch.uint8)
         return npairs
 
+    def get_pairlist(self):
+        return self.pairs
+
     def ed_forces(self):
         self._pull()
         for t in range(self.t0, self.t1):
@@ -107,16 +110,16 @@ class OracleBackend:
     def sync(self): pass
 
 
-def _worker(rank, world, port, q, replicate):
+def _worker(rank, world, port, q, replicate, halo=False, n_tet=30):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     pkg = importlib.import_module("msc-project_b200")
     dmod = importlib.import_module("msc-project_b200.dist")
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    system = pkg.make_ring(30, kind="coil", laps=2, lap_gap=9.0)
+    system = pkg.make_ring(n_tet, kind="coil", laps=2, lap_gap=9.0)
     b = OracleBackend(po, system)
-    sh = dmod.ShardedEngine(b, dist, system.n, rank, world, replicate=replicate)
+    sh = dmod.ShardedEngine(b, dist, system.n, rank, world, replicate=replicate, halo=halo)
     npairs = sh.build_pairlist()
     sh.step(2, 0)
     sh.merge()
@@ -124,7 +127,8 @@ def _worker(rank, world, port, q, replicate):
     b._pull()
     c, v = b.o.get_state()
     if rank == 0:
-        q.put((npairs, c, v, (sh.plan.t0, sh.plan.t1, sh.plan.p0, sh.plan.p1)))
+        halo_rows = int(sh.halo_plan.recv_idx.size) if sh.halo_plan is not None else -1
+        q.put((npairs, c, v, (sh.plan.t0, sh.plan.t1, sh.plan.p0, sh.plan.p1), halo_rows))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -137,7 +141,7 @@ def test_sharded_protocol_world2_equals_single_rank(edmd, po, replicate):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q, replicate)) for r in range(2)]
     for p in procs:
         p.start()
-    npairs, c, v, plan = q.get(timeout=600)
+    npairs, c, v, plan, _ = q.get(timeout=600)
     for p in procs:
         p.join(timeout=600)
         assert p.exitcode == 0
@@ -159,3 +163,42 @@ def test_shard_plan_covers_everything_once(edmd):
             seen_t[pl.t0:pl.t1] += 1; seen_p[pl.p0:pl.p1] += 1
             assert pl.t1 - pl.t0 <= pl.t_chunk and pl.p1 - pl.p0 <= pl.p_chunk
         assert np.all(seen_t == 1) and np.all(seen_p == 1)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_halo_exchange_equals_single_rank(edmd, po, world):
+    """Sparse per-step exchange (variable-size all-to-all of the tetrad blocks a rank reads) instead
+    of the coordinate all-gather; uneven blocks at world 3."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 20 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, False, True, 40)) for r in range(world)]
+    for p in procs:
+        p.start()
+    npairs, c, v, plan, halo_rows = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    system = edmd.make_ring(40, kind="coil", laps=2, lap_gap=9.0)
+    o = po.Oracle(system, "port")
+    assert o.build_pairs() == npairs
+    o.step(2); o.merge()
+    co, vo = o.get_state()
+    assert np.array_equal(c, co) and np.array_equal(v, vo)
+    assert 0 < halo_rows < system.n          # a real, partial halo
+
+
+def test_halo_plan_lists(edmd):
+    dmod = importlib.import_module("msc-project_b200.dist")
+    n, world = 100, 4
+    pairs = np.array([(i, (i + d) % n) for i in range(n) for d in (6, 7, 8) if (i + d) < n], dtype=np.int32)
+    for r in range(world):
+        pl = dmod.ShardPlan(n, len(pairs), world, r)
+        hp = dmod.HaloPlan(pairs, n, world, r, (pl.t0, pl.t1), (pl.p0, pl.p1))
+        used = set(pairs[pl.p0:pl.p1].ravel().tolist())
+        for a, b in pairs:
+            if pl.t0 <= a < pl.t1: used.add(int(b))
+            if pl.t0 <= b < pl.t1: used.add(int(a))
+        want = sorted(t for t in used if not (pl.t0 <= t < pl.t1))
+        assert hp.recv_idx.tolist() == want
+        assert hp.recv_counts.sum() == len(want)

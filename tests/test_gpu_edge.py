@@ -164,3 +164,29 @@ def test_c2_size_coil_random_on(edmd, po):
         z_o = o.get_forces()["rnd"] / np.sqrt(ps_o.masses3)
         z_g = f["rnd"][s.off3[t]:s.off3[t + 1]] / np.sqrt(ps_t.masses3)
         assert np.allclose(z_g, z_o, rtol=1e-14)
+
+
+@pytest.mark.parametrize("kind,n", [("coil", 600), ("ring", 3000)])
+def test_cell_list_builder_equals_sweep_and_oracle(edmd, po, kind, n):
+    """The uniform-grid builder must return the reference's list: same pairs, same orientation, same order."""
+    s = edmd.make_ring(n, kind=kind, laps=6, lap_gap=9.0)
+    g = edmd.Engine(s)
+    g.set_pair_builder(1); n1 = g.build_pairlist(); p1 = g.get_pairlist()
+    g.set_pair_builder(2); n2 = g.build_pairlist(); p2 = g.get_pairlist()
+    assert n1 == n2 and np.array_equal(p1, p2)
+    o = po.Oracle(s, "port")
+    assert o.build_pairs() == n2 and np.array_equal(o.get_pairs(), p2)
+
+
+def test_cell_list_builder_large_ring(edmd):
+    """2e5 tetrads: auto-selected cell list; every tetrad of the planar ring has the same partner count."""
+    s = edmd.make_ring(200000, kind="ring")
+    g = edmd.Engine(s)
+    npairs = g.build_pairlist()
+    p = g.get_pairlist()
+    deg = np.bincount(p.reshape(-1), minlength=s.n)
+    assert 4 * s.n <= npairs <= 5 * s.n + 5                # separations 6..9 (or ..10) either side
+    assert deg.max() - deg.min() <= 2
+    sep = np.abs(p[:, 0] - p[:, 1]); sep = np.minimum(sep, s.n - sep)
+    assert sep.min() == 6
+    assert np.all(np.diff(np.minimum(p[:, 0], p[:, 1])) >= 0)     # rows ascending

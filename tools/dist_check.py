@@ -12,7 +12,7 @@ for name, s in (("coil64", pkg.make_ring(64 * 10 // 10 if False else 60, kind="c
                 ("coil200-uneven", pkg.make_ring(200 if world != 3 else 200, kind="coil", laps=4, lap_gap=9.0))):
     g = pkg.Engine(s, device=local)
     sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world,
-                            replicate=(name == "coil64"))
+                            replicate=(name == "coil64"), halo=True)
     npairs = sh.build_pairlist()
     sh.set_rng(1000000000, 1, 0)
     sh.step(5, 1)
