@@ -82,8 +82,9 @@ int  edmd_set_nb_consts(edmd_engine* e, double krep, double qfac);
 int  edmd_set_nb_clip(edmd_engine* e, int on);
 /* Arithmetic form of the NB distance pass (nb_scan_kernel): 0 = direct differences exactly
  * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (default; 4 instead of
- * 6 FP64 instructions per atom pair).  The pass only selects tetrad pairs for the exact
- * force kernel, so forces and energies are bit-identical in both modes. */
+ * 6 FP64 instructions per atom pair), 2 = the same test in FP32 with packed FFMA2 and a proven
+ * error margin (the "FP32 variant" of BASELINE configs[4]).  The pass only selects tetrad pairs
+ * for the exact FP64 force kernel, so forces and energies are bit-identical in all modes. */
 int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
 
 /* ---- data in / out ----------------------------------------------------------------- */

@@ -420,7 +420,7 @@ int edmd_set_nb_clip(edmd_engine* e, int on) {
 
 int edmd_set_nb_scan_mode(edmd_engine* e, int mode) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
-    if (mode != 0 && mode != 1) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram)", mode);
+    if (mode < 0 || mode > 2) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram, 2 fp32 prefilter)", mode);
     e->scan_mode = mode;
     return 0;
 }
