@@ -166,6 +166,8 @@ int edmd_get_energies(edmd_engine* e, double out[4]);
  * from the value passed to edmd_set_rng. */
 int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before);
 int edmd_step(edmd_engine* e, int nsteps, int random_mode);
+/* edmd_step replays a CUDA graph of one step (on by default; off: plain kernel launches). */
+int edmd_set_graph(edmd_engine* e, int on);
 int edmd_sync(edmd_engine* e);
 
 /* ---- introspection (bench / multi-GPU plumbing) -------------------------------------- */

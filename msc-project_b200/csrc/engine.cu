@@ -115,6 +115,11 @@ struct edmd_engine {
     long calls = 0;
 
     int scan_mode = 1;   // 0 direct, 1 gram (see nb.cu)
+    // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
+    bool use_graph = true, graph_valid = false;
+    int graph_random_mode = -1;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+    long* d_calls = nullptr;   // device copy of the random-stream call counter
     int nb_clip = 1;     // clip summed NB force components to [-1,1] (master.cpp:304-305)
     cudaEvent_t span0 = nullptr, span1 = nullptr;   // edmd_timer_start/stop
     std::vector<cudaEvent_t> marks;                 // edmd_mark / edmd_mark_elapsed
@@ -152,7 +157,10 @@ void timer_fold(edmd_engine* e, int id) {
     t.ev.clear();
 }
 
+void drop_graph(edmd_engine* e);
 void free_system(edmd_engine* e) {
+    drop_graph(e);
+    cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -246,6 +254,12 @@ int check_ready(edmd_engine* e, bool need_pairs) {
     return 0;
 }
 
+void drop_graph(edmd_engine* e) {
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
+    e->graph_valid = false;
+}
+
 // Owned tetrads sorted (stably) by parameter set: consecutive tetrads of a CTA's run share the
 // eigenvector registers in ed_project_kernel.
 int upload_order(edmd_engine* e) {
@@ -311,7 +325,7 @@ int do_finish(edmd_engine* e) {
     e->latest_in_crd2 = true;
     return 0;
 }
-int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before) {
+int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before, const long* calls_dev = nullptr) {
     if (mode == 0) {
         if (!e->rnd_zero) {
             CK(cudaMemsetAsync(e->rnd, 0, sizeof(double) * (size_t)e->n * 3 * e->S, e->st));
@@ -322,7 +336,7 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before)
     if (mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown (0 = off, 1 = reference stream)", mode);
     timer_begin(e, T_RNG);
     CK(launch_random_terms(e->ps, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
-                           calls_before + e->t0, e->st));
+                           calls_before + e->t0, calls_dev, e->st));
     timer_end(e, T_RNG, 1);
     e->rnd_zero = false;
     return 0;
@@ -402,6 +416,7 @@ int edmd_set_params(edmd_engine* e, const edmd_params* p) {
     e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
     e->sp.mole_least = p->mole_Least;
     e->hits_valid = false;
+    drop_graph(e);
     return 0;
 }
 
@@ -409,12 +424,14 @@ int edmd_set_nb_consts(edmd_engine* e, double krep, double qfac) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->sp.krep = krep; e->sp.qfac = qfac;
     e->hits_valid = false;
+    drop_graph(e);
     return 0;
 }
 
 int edmd_set_nb_clip(edmd_engine* e, int on) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->nb_clip = on ? 1 : 0;
+    drop_graph(e);
     return 0;
 }
 
@@ -422,6 +439,7 @@ int edmd_set_nb_scan_mode(edmd_engine* e, int mode) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     if (mode < 0 || mode > 2) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram, 2 fp32 prefilter)", mode);
     e->scan_mode = mode;
+    drop_graph(e);
     return 0;
 }
 
@@ -769,7 +787,7 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     CK(cudaStreamSynchronize(e->st));
     e->np = np;
     if (int rc = build_adjacency(e, pairs)) return rc;
-    e->have_pairs = true; e->hits_valid = false;
+    e->have_pairs = true; e->hits_valid = false; drop_graph(e);
     if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
     if (num_pairs) *num_pairs = np;
     return 0;
@@ -801,7 +819,7 @@ int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long np) {
     if (np) CK(cudaMemcpy(e->d_pairs, pv.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
     e->np = np;
     if (int rc = build_adjacency(e, pv)) return rc;
-    e->have_pairs = true; e->hits_valid = false;
+    e->have_pairs = true; e->hits_valid = false; drop_graph(e);
     if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
     return 0;
 }
@@ -813,6 +831,7 @@ int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
     const bool range_changed = (t0 != e->t0 || t1 != e->t1);
+    drop_graph(e);
     e->t0 = t0; e->t1 = t1; e->p0 = p0; e->p1 = p1; e->shard_pairs_custom = true;
     e->hits_valid = false;
     if (range_changed) return upload_order(e);
@@ -916,19 +935,66 @@ int edmd_get_energies(edmd_engine* e, double out[4]) {
 int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->time0 = time0; e->rank = rank; e->calls = calls_before;
+    drop_graph(e);
+    return 0;
+}
+
+static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
+    if (int rc = do_ed(e)) return rc;
+    if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
+    if (random_mode == 1 && calls_dev) CK(launch_bump_counter(e->d_calls, (long)e->n, e->st));
+    if (int rc = do_scan(e)) return rc;
+    return do_finish(e);
+}
+
+int edmd_set_graph(edmd_engine* e, int on) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->use_graph = on != 0;
+    if (!on) drop_graph(e);
     return 0;
 }
 
 int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (int rc = check_ready(e, true)) return rc;
+    if (random_mode != 0 && random_mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown", random_mode);
     CK(cudaSetDevice(e->device));
-    for (int it = 0; it < nsteps; it++) {
-        if (int rc = do_ed(e)) return rc;
-        if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls)) return rc;
-        if (random_mode == 1) e->calls += e->n;
-        if (int rc = do_scan(e)) return rc;
-        if (int rc = do_finish(e)) return rc;
+    const bool graph_ok = e->use_graph && !e->timing && e->nb_clip && nsteps > 1;
+    if (!graph_ok) {
+        for (int it = 0; it < nsteps; it++) {
+            if (int rc = one_step(e, random_mode, nullptr)) return rc;
+            if (random_mode == 1) e->calls += e->n;
+        }
+        e->hits_valid = false;
+        return 0;
     }
+    // Graph replay: one captured step = {superpose, project, [random, counter bump], memset, scan, finish}.
+    // The captured ED pass reads the post-integrate buffer (crd2), so make that the current one first;
+    // mode 0 needs the random-term planes zeroed once, outside the graph.
+    if (!e->latest_in_crd2) {
+        const size_t off = (size_t)e->t0 * 3 * e->S, cnt = (size_t)(e->t1 - e->t0) * 3 * e->S;
+        if (cnt) CK(cudaMemcpyAsync(e->crd2 + off, e->crd + off, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e->st));
+        e->latest_in_crd2 = true;
+    }
+    if (random_mode == 0) { if (int rc = do_random(e, 0, 0, 0, 0)) return rc; }
+    if (!e->d_calls) CK(dev_alloc(&e->d_calls, 1));
+    CK(cudaMemcpyAsync(e->d_calls, &e->calls, sizeof(long), cudaMemcpyHostToDevice, e->st));
+    if (!e->graph_valid || e->graph_random_mode != random_mode) {
+        drop_graph(e);
+        CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+        const bool zero_flag = e->rnd_zero;
+        int rc = one_step(e, random_mode, e->d_calls);
+        cudaError_t end = cudaStreamEndCapture(e->st, &e->graph);
+        e->rnd_zero = random_mode == 0 ? zero_flag : false;
+        if (rc) { if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; } return rc; }
+        CK(end);
+        CK(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+        e->graph_valid = true; e->graph_random_mode = random_mode;
+        e->latest_in_crd2 = true;
+    }
+    for (int it = 0; it < nsteps; it++) CK(cudaGraphLaunch(e->graph_exec, e->st));
+    e->launches += (long long)nsteps * (random_mode == 1 ? 6 : 4);
+    if (random_mode == 1) { e->calls += (long)nsteps * e->n; e->rnd_zero = false; }
+    e->latest_in_crd2 = true;
     e->hits_valid = false;
     return 0;
 }

@@ -57,7 +57,8 @@ cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const 
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                cudaStream_t st);
+                                const long* calls_dev, cudaStream_t st);
+cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st);
 
 // interleaved xyz (reference layout, tetrads concatenated at off3[t]) <-> SoA planes
 cudaError_t launch_pack_planes(const double* flat, const long long* off3, const int* natoms, double* planes,

@@ -41,6 +41,7 @@ struct RngArgs {
     long time0;
     int rank;
     long calls_before;   // calculate_Random_Terms calls made before tetrad t0 of this launch
+    const long* calls_dev;   // when non-null: *calls_dev + t0 replaces calls_before (CUDA-graph replay)
 };
 
 __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
 
     // seed: RNG_Seed starts at 13579, ++ per call, reset to 13579 once it exceeds 50,000,000
     // (edmd.cpp:173,179-180): the value used by call number c (0-based) is 13579 + c % 49986422.
-    const long c = A.calls_before + w;
+    const long c = (A.calls_dev ? *A.calls_dev + A.t0 : A.calls_before) + w;
     const unsigned rs = 13579u + (unsigned)(c % 49986422L);
     unsigned seed = (unsigned)((long)(rs + (unsigned)(A.rank * A.rank * A.rank)) + A.time0);
     if (seed == 0) seed = 1;
@@ -118,11 +119,17 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
 
 cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                cudaStream_t st) {
+                                const long* calls_dev, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    RngArgs A{ps, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before};
+    RngArgs A{ps, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before, calls_dev};
     const int wpb = 4;
     random_terms_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+__global__ void bump_counter_kernel(long* counter, long by) { *counter += by; }
+cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st) {
+    bump_counter_kernel<<<1, 1, 0, st>>>(counter, by);
     return cudaGetLastError();
 }
 

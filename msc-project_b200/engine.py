@@ -98,6 +98,7 @@ def load_library():
         "edmd_get_energies": (C.c_int, [E, PD]),
         "edmd_set_rng": (C.c_int, [E, C.c_long, C.c_int, C.c_long]),
         "edmd_step": (C.c_int, [E, C.c_int, C.c_int]),
+        "edmd_set_graph": (C.c_int, [E, C.c_int]),
         "edmd_sync": (C.c_int, [E]),
         "edmd_device_buffer": (C.c_int, [E, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         "edmd_atom_stride": (C.c_int, [E]),
@@ -373,6 +374,9 @@ class Engine:
 
     def step(self, nsteps=1, random_mode=0):
         self._ck(self.lib.edmd_step(self.h, nsteps, random_mode))
+
+    def set_graph(self, on: bool):
+        self._ck(self.lib.edmd_set_graph(self.h, int(on)))
 
     def sync(self):
         self._ck(self.lib.edmd_sync(self.h))

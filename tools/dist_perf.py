@@ -10,8 +10,10 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = int(sys.argv[1]); mode = sys.argv[2] if len(sys.argv) > 2 else "halo"; steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
 random_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+scan_mode = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 s = pkg.make_ring(n, kind="ring")
 g = pkg.Engine(s, device=local)
+g.set_nb_scan_mode(scan_mode)
 sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist if world > 1 else None, s.n, rank, world,
                         replicate=(mode == "replicate"), halo=(mode == "halo"))
 t0 = time.time(); npairs = sh.build_pairlist(); tb = time.time() - t0
@@ -25,6 +27,6 @@ if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
 k = {nm: (lambda r: r[0] / r[1] if r[1] else None)(g.timing_get(i)) for nm, i in (("ed", 0), ("scan", 1), ("finish", 2), ("rng", 3))}
 if rank == 0:
     halo = sh.halo_plan.recv_idx.size if sh.halo_plan is not None else None
-    print(f"n={n} world={world} mode={mode} random={random_mode} pairs={npairs} build={tb:.2f}s step={float(t):.3f} ms  kernels(ms/launch)={k} halo_rows={halo}", flush=True)
+    print(f"n={n} world={world} mode={mode} scan_mode={scan_mode} random={random_mode} pairs={npairs} build={tb:.2f}s step={float(t):.3f} ms  kernels(ms/launch)={k} halo_rows={halo}", flush=True)
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
