@@ -78,6 +78,7 @@ struct edmd_engine {
     double* crd2 = nullptr;        // post-integrate coordinates written by the fused finish kernel
     bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
+    unsigned char *d_mark = nullptr, *d_dirty = nullptr;   // per-tetrad: in a flagged pair now / fnb non-zero
     bool rnd_zero = true;   // random terms currently all zero
 
     // staging (interleaved flat), 3 slots
@@ -161,6 +162,7 @@ void drop_graph(edmd_engine* e);
 void free_system(edmd_engine* e) {
     drop_graph(e);
     cudaFree(e->d_calls); e->d_calls = nullptr;
+    cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -301,6 +303,7 @@ int do_scan(edmd_engine* e) {
     return 0;
 }
 int do_accumulate(edmd_engine* e, int use_hits) {
+    CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)e->n, e->st));
     timer_begin(e, T_ACC);
     CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off,
                             e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
@@ -318,10 +321,11 @@ int do_finish(edmd_engine* e) {
         return do_integrate(e, 1, 1);
     }
     timer_begin(e, T_ACC);
-    CK(launch_nb_finish(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off, e->d_adj_partner,
-                        e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
-                        e->rnd_zero ? nullptr : e->rnd, e->temp, e->t0, e->t1 - e->t0, e->S, e->sp, e->st));
-    timer_end(e, T_ACC, 1);
+    CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_pairs, e->np, e->d_adj_off,
+                              e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
+                              e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n, e->t0,
+                              e->t1 - e->t0, e->S, e->sp, e->st));
+    timer_end(e, T_ACC, 3);
     e->latest_in_crd2 = true;
     return 0;
 }
@@ -526,6 +530,8 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
+    CK(dev_alloc(&e->d_mark, (size_t)n)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)n, e->st));   // unknown force contents: treat as dirty
     CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
     CK(dev_alloc(&e->d_stage, 3 * (size_t)e->total3));
     CK(cudaMallocHost((void**)&e->h_stage, sizeof(double) * 3 * (size_t)e->total3));
@@ -706,6 +712,7 @@ int edmd_set_forces(edmd_engine* e, const edmd_tetrad* tets, int n) {
     if (int rc = stage_in(e, e->fed, 0)) return rc;
     if (int rc = stage_in(e, e->rnd, 1)) return rc;
     if (int rc = stage_in(e, e->fnb, 2)) return rc;
+    CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)e->n, e->st));
     CK(cudaStreamSynchronize(e->st));
     e->rnd_zero = false;
     return 0;
@@ -992,7 +999,7 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
         e->latest_in_crd2 = true;
     }
     for (int it = 0; it < nsteps; it++) CK(cudaGraphLaunch(e->graph_exec, e->st));
-    e->launches += (long long)nsteps * (random_mode == 1 ? 6 : 4);
+    e->launches += (long long)nsteps * (random_mode == 1 ? 8 : 6);
     if (random_mode == 1) { e->calls += (long)nsteps * e->n; e->rnd_zero = false; }
     e->latest_in_crd2 = true;
     e->hits_valid = false;

@@ -32,6 +32,13 @@ cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int*
                              double* crd_out, const double* fed, const double* rnd, double* temp, int t0, int count,
                              int S, const SimParams& sp, cudaStream_t st);
 
+cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
+                                   const unsigned char* hit, const int2* pairs, long long np, const long long* adj_off,
+                                   const int* adj_partner, const int* adj_pair, double* fnb, double* e_nb,
+                                   const ParamSets& ps, double* vel, double* crd_out, const double* fed,
+                                   const double* rnd, double* temp, unsigned char* mark, unsigned char* dirty, int n,
+                                   int t0, int count, int S, const SimParams& sp, cudaStream_t st);
+
 cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
                              const double* fed, const double* rnd, const double* fnb, double* temp,
                              int t0, int count, int do_vel, int do_crd, const SimParams& sp,

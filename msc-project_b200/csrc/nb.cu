@@ -515,6 +515,8 @@ __global__ void __launch_bounds__(kThreads, 4) nb_finish_kernel(AccArgs A, IntAr
     const int t = A.t0 + blockIdx.x;
     double f[3];
     nb_accumulate_tetrad(A, t, sm, f);
+    // (loading the integrate operands before the flag scan was tried: the extra live registers
+    // spill and the kernel gets slower — 1.41 vs 1.27 ms at 1e5 tetrads)
     integrate_tetrad(I, t, f, red);
 }
 
@@ -527,6 +529,67 @@ cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int
     AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
               cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, use_hits, clip};
     nb_accumulate_kernel<<<count, kThreads, 0, st>>>(A);
+    return cudaGetLastError();
+}
+
+// ---- per-tetrad hit marks ------------------------------------------------------------------------
+// tet_mark[t] = 1 iff tetrad t takes part in at least one flagged pair.  Almost every tetrad has none,
+// and then the tail of the step is a pure streaming update: the fused kernel is split into a lean
+// kernel for unmarked tetrads (few registers, 6 CTAs/SM, no adjacency walk) and the full kernel for
+// marked ones; both are launched over all owned tetrads and return at once for the other's share.
+__global__ void mark_tetrads_kernel(const unsigned char* hit, const int2* pairs, long long np, unsigned char* mark) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        if (hit[p]) { const int2 pr = pairs[p]; mark[pr.x] = 1; mark[pr.y] = 1; }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const unsigned char* mark,
+                                                                    unsigned char* dirty, double* fnb, double* e_nb) {
+    __shared__ double red[1][kWarps];
+    const int t = I.t0 + blockIdx.x;
+    if (mark[t]) return;
+    const int S = I.ps.S;
+    if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
+        for (int k = threadIdx.x; k < 3 * S; k += blockDim.x) fnb[(size_t)t * 3 * S + k] = 0.0;
+        if (threadIdx.x == 0) { e_nb[2 * (size_t)t] = 0.0; e_nb[2 * (size_t)t + 1] = 0.0; dirty[t] = 0; }
+    }
+    const double zero[3] = {0.0, 0.0, 0.0};
+    integrate_tetrad(I, t, zero, red);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) finish_marked_kernel(AccArgs A, IntArgs I, const unsigned char* mark,
+                                                                  unsigned char* dirty) {
+    __shared__ AccSmem sm;
+    __shared__ double red[1][kWarps];
+    const int t = A.t0 + blockIdx.x;
+    if (!mark[t]) return;
+    double f[3];
+    nb_accumulate_tetrad(A, t, sm, f);
+    if (threadIdx.x == 0) dirty[t] = 1;
+    integrate_tetrad(I, t, f, red);
+}
+
+cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
+                                   const unsigned char* hit, const int2* pairs, long long np, const long long* adj_off,
+                                   const int* adj_partner, const int* adj_pair, double* fnb, double* e_nb,
+                                   const ParamSets& ps, double* vel, double* crd_out, const double* fed,
+                                   const double* rnd, double* temp, unsigned char* mark, unsigned char* dirty, int n,
+                                   int t0, int count, int S, const SimParams& sp, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    cudaError_t err = cudaMemsetAsync(mark, 0, (size_t)n, st);
+    if (err != cudaSuccess) return err;
+    if (np > 0) {
+        long long blocks = (np + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        mark_tetrads_kernel<<<(int)blocks, 256, 0, st>>>(hit, pairs, np, mark);
+    }
+    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
+    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
+              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1, 1};
+    IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
+    finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
+    finish_marked_kernel<<<count, kThreads, 0, st>>>(A, I, mark, dirty);
     return cudaGetLastError();
 }
 
