@@ -115,118 +115,145 @@ __device__ void qcp_rotation(double R[9], const double M[9], double e0) {
     R[6] = 2 * (ki + wj);     R[7] = 2 * (jk - wi);     R[8] = w2 - i2 - j2 + k2;
 }
 
-constexpr int kSupThreads = 64;
+constexpr int kSupThreads = 128;                 // one CTA = TWO tetrads (64 threads each)
 constexpr int kSupWords = 24;   // per tetrad: R[9], shift[3], avg centroid[3], x centroid[3], pad
+constexpr int kSupRow = kMaxStride + 1;           // +1: lanes k = 0..10 hit distinct banks
 
 struct SupArgs {
     ParamSets ps;
     const int* param_id;
     const double* crd;   // [n][3][S]
     double* sup;         // [n][kSupWords] out
-    int t0;
+    int t0, count;
 };
 
-// lane k < nsum: running sum of buf[k][0..na) in atom order, starting from 0.0
-// rows are padded by one double so that lanes k = 0..10 hit distinct shared-memory banks
-constexpr int kSupRow = kMaxStride + 1;
-__device__ __forceinline__ double seq_sum(const double (*buf)[kSupRow], int k, int nsum, int na) {
+// Running sum, in atom order and starting from 0.0, of  (p1*q1 + p2*q2) + p3*q3  over i < na.
+// With p2 = p3 = a row of zeros this is the plain product sum p1*q1 (adding +0.0 is exact), with
+// q = a row of ones and p2 = p3 = zeros the plain sum of p1.  8 elements' loads and products are
+// issued before their 8 dependent adds, so the chain runs at DADD latency.
+__device__ __forceinline__ double seq_sum3(const double* p1, const double* q1, const double* p2, const double* q2,
+                                           const double* p3, const double* q3, int na) {
     double s = 0.0;
-    if (k < nsum) {
-        const double* row = buf[k];
-        int i = 0;
-        // 8 independent shared-memory loads in flight, then the 8 dependent adds: the chain runs at
-        // DADD latency instead of LDS + DADD latency per element
-        for (; i + 8 <= na; i += 8) {
-            const double v0 = row[i], v1 = row[i + 1], v2 = row[i + 2], v3 = row[i + 3];
-            const double v4 = row[i + 4], v5 = row[i + 5], v6 = row[i + 6], v7 = row[i + 7];
-            s = s + v0; s = s + v1; s = s + v2; s = s + v3;
-            s = s + v4; s = s + v5; s = s + v6; s = s + v7;
-        }
-        for (; i < na; i++) s = s + row[i];
+    int i = 0;
+    for (; i + 8 <= na; i += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = (p1[i + u] * q1[i + u] + p2[i + u] * q2[i + u]) + p3[i + u] * q3[i + u];
+#pragma unroll
+        for (int u = 0; u < 8; u++) s = s + v[u];
     }
+    for (; i < na; i++) s = s + ((p1[i] * q1[i] + p2[i] * q2[i]) + p3[i] * q3[i]);
+    return s;
+}
+__device__ __forceinline__ double seq_sum1(const double* p, int na) {
+    double s = 0.0;
+    int i = 0;
+    for (; i + 8 <= na; i += 8) {
+        const double v0 = p[i], v1 = p[i + 1], v2 = p[i + 2], v3 = p[i + 3];
+        const double v4 = p[i + 4], v5 = p[i + 5], v6 = p[i + 6], v7 = p[i + 7];
+        s = s + v0; s = s + v1; s = s + v2; s = s + v3; s = s + v4; s = s + v5; s = s + v6; s = s + v7;
+    }
+    for (; i < na; i++) s = s + p[i];
     return s;
 }
 
-__global__ void __launch_bounds__(kSupThreads) superpose_kernel(SupArgs A) {
-    __shared__ double buf[11][kSupRow];
-    __shared__ double sC[6];
-    __shared__ double sR[9];
-    const int t = A.t0 + blockIdx.x;
+// Two tetrads per CTA: threads 0-63 serve tetrad A, 64-127 tetrad B (4 atoms each) for the parallel
+// parts; the sequential sums of BOTH tetrads run in warp 0 — lanes 0-15 tetrad A, lanes 16-31
+// tetrad B — so one instruction stream advances 2 x 11 chains.  18 tetrads resident per SM.
+__global__ void __launch_bounds__(kSupThreads, 9) superpose_kernel(SupArgs A) {
+    __shared__ double buf[2][6][kSupRow];   // rows 0-2: avg (then centred), rows 3-5: x (then centred)
+    __shared__ double zero_row[kSupRow];
+    __shared__ double sC[2][6];
+    __shared__ double sR[2][9];
     const int tid = threadIdx.x, lane = tid & 31;
+    const int g = tid >> 6, gt = tid & 63;             // tetrad slot of this thread, thread index inside it
+    const int S = A.ps.S;
+    const int e = 2 * blockIdx.x + g;
+    const bool have = e < A.count;
+    const int t = A.t0 + (have ? e : 2 * blockIdx.x);  // slot B of an odd tail repeats tetrad A (results unused)
     const int ps = A.param_id[t];
     const int na = A.ps.na[ps];
-    const int S = A.ps.S;
     const double* X = A.crd + (size_t)t * 3 * S;
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
-    constexpr int R4 = kMaxStride / kSupThreads;   // atoms per thread
+    constexpr int R4 = kMaxStride / 64;
 
-    double x[R4][3], a[R4][3];
+    for (int i = tid; i < kSupRow; i += kSupThreads) zero_row[i] = 0.0;
 #pragma unroll
     for (int r = 0; r < R4; r++) {
-        const int i = tid + kSupThreads * r;
+        const int i = gt + 64 * r;
         if (i < na) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) {
-                a[r][c] = AV[c * S + i]; x[r][c] = X[c * S + i];
-                buf[c][i] = a[r][c]; buf[3 + c][i] = x[r][c];
-            }
+            for (int c = 0; c < 3; c++) { buf[g][c][i] = AV[c * S + i]; buf[g][3 + c][i] = X[c * S + i]; }
         }
     }
     __syncthreads();
-    if (tid < 32) {   // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
-        const double s = seq_sum(buf, lane, 6, na);
-        if (lane < 6) sC[lane] = s / na;
+    // chain lanes: half h = lane / 16 works on tetrad slot h with its own atom count
+    const int h = lane >> 4, k = lane & 15;
+    int na_h = na;
+    if (tid < 32) {
+        const int eh = 2 * blockIdx.x + h;
+        const int th = A.t0 + (eh < A.count ? eh : 2 * blockIdx.x);
+        na_h = A.ps.na[A.param_id[th]];
+        // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
+        const double s = seq_sum1(buf[h][k < 6 ? k : 0], na_h);
+        if (k < 6) sC[h][k] = s / na_h;
     }
     __syncthreads();
     double ca[3], cx[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) { ca[c] = sC[c]; cx[c] = sC[3 + c]; }
+    for (int c = 0; c < 3; c++) { ca[c] = sC[g][c]; cx[c] = sC[g][3 + c]; }
 #pragma unroll
-    for (int r = 0; r < R4; r++) {   // InnerProduct terms, qcprot.c:134-156
-        const int i = tid + kSupThreads * r;
+    for (int r = 0; r < R4; r++) {   // centre in place (qcprot.c:382-386)
+        const int i = gt + 64 * r;
         if (i < na) {
-            const double a0 = a[r][0] - ca[0], a1 = a[r][1] - ca[1], a2 = a[r][2] - ca[2];
-            const double x0 = x[r][0] - cx[0], x1 = x[r][1] - cx[1], x2 = x[r][2] - cx[2];
-            buf[0][i] = (a0 * x0); buf[1][i] = (a0 * x1); buf[2][i] = (a0 * x2);
-            buf[3][i] = (a1 * x0); buf[4][i] = (a1 * x1); buf[5][i] = (a1 * x2);
-            buf[6][i] = (a2 * x0); buf[7][i] = (a2 * x1); buf[8][i] = (a2 * x2);
-            buf[9][i] = a0 * a0 + a1 * a1 + a2 * a2;
-            buf[10][i] = (x0 * x0 + x1 * x1 + x2 * x2);
+#pragma unroll
+            for (int c = 0; c < 3; c++) { buf[g][c][i] = buf[g][c][i] - ca[c]; buf[g][3 + c][i] = buf[g][3 + c][i] - cx[c]; }
         }
     }
     __syncthreads();
-    if (tid < 32) {
-        const double s = seq_sum(buf, lane, 11, na);
+    if (tid < 32) {   // InnerProduct, qcprot.c:132-157: lanes 0-8 the 3x3 products, 9 and 10 the two norms
+        const double* z = zero_row;
+        const double *p1, *q1, *p2 = z, *q2 = z, *p3 = z, *q3 = z;
+        if (k < 9) { p1 = buf[h][k / 3]; q1 = buf[h][3 + k % 3]; }
+        else if (k == 9) { p1 = q1 = buf[h][0]; p2 = q2 = buf[h][1]; p3 = q3 = buf[h][2]; }
+        else if (k == 10) { p1 = q1 = buf[h][3]; p2 = q2 = buf[h][4]; p3 = q3 = buf[h][5]; }
+        else { p1 = q1 = z; }
+        const double s = seq_sum3(p1, q1, p2, q2, p3, q3, na_h);
         double m[11];
 #pragma unroll
-        for (int k = 0; k < 11; k++) m[k] = __shfl_sync(0xffffffffu, s, k);
+        for (int j = 0; j < 11; j++) m[j] = __shfl_sync(0xffffffffu, s, (lane & 16) + j);
         double R[9];
         qcp_rotation(R, m, (m[9] + m[10]) * 0.5);
-        if (lane == 0) {
+        if (k == 0) {
 #pragma unroll
-            for (int k = 0; k < 9; k++) sR[k] = R[k];
+            for (int j = 0; j < 9; j++) sR[h][j] = R[j];
         }
     }
     __syncthreads();
     double R[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = sR[k];
+    for (int j = 0; j < 9; j++) R[j] = sR[g][j];
 #pragma unroll
-    for (int r = 0; r < R4; r++) {   // offset-vector terms on the UNCENTRED arrays, edmd.cpp:97-101
-        const int i = tid + kSupThreads * r;
+    for (int r = 0; r < R4; r++) {   // offset-vector terms on the UNCENTRED arrays (re-read, L2-resident), edmd.cpp:97-101
+        const int i = gt + 64 * r;
         if (i < na) {
-            buf[0][i] = (a[r][0] - (R[0] * x[r][0] + R[1] * x[r][1] + R[2] * x[r][2]));
-            buf[1][i] = (a[r][1] - (R[3] * x[r][0] + R[4] * x[r][1] + R[5] * x[r][2]));
-            buf[2][i] = (a[r][2] - (R[6] * x[r][0] + R[7] * x[r][1] + R[8] * x[r][2]));
+            const double a0 = AV[i], a1 = AV[S + i], a2 = AV[2 * S + i];
+            const double x0 = X[i], x1 = X[S + i], x2 = X[2 * S + i];
+            buf[g][0][i] = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
+            buf[g][1][i] = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
+            buf[g][2][i] = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
         }
     }
     __syncthreads();
     if (tid < 32) {
-        const double s = seq_sum(buf, lane, 3, na);
-        double* out = A.sup + (size_t)t * kSupWords;
-        if (lane < 3) out[9 + lane] = s / na;          // edmd.cpp:102
-        if (lane < 9) out[lane] = R[lane];
-        if (lane < 6) out[12 + lane] = sC[lane];
+        const double s = seq_sum1(buf[h][k < 3 ? k : 0], na_h);
+        const int eh = 2 * blockIdx.x + h;
+        if (eh < A.count) {
+            double* out = A.sup + (size_t)(A.t0 + eh) * kSupWords;
+            if (k < 3) out[9 + k] = s / na_h;          // edmd.cpp:102
+            if (k < 9) out[k] = sR[h][k];
+            if (k < 6) out[12 + k] = sC[h][k];
+        }
     }
 }
 
@@ -441,8 +468,8 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                              cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    SupArgs B{ps, param_id, crd_in, sup, t0};
-    superpose_kernel<<<count, kSupThreads, 0, st>>>(B);
+    SupArgs B{ps, param_id, crd_in, sup, t0, count};
+    superpose_kernel<<<(count + 1) / 2, kSupThreads, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer

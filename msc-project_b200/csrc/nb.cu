@@ -70,6 +70,9 @@ constexpr int kScanCtasPerSm = 12;
 // for 2 cycles): per atom pair MODE 0 issues 6 FP64 + 0.375 LDS.128 + 0.5 VIMNMX3, MODE 1 issues
 // 3 FP64 + 0.5 LDS.128 + 0.5 VIMNMX3 — the 4-atom register tile is what keeps the non-FP64 share
 // small (the first version of this kernel, 1 atom per thread, was dispatch-bound at 80 % FP64).
+// (Tried and rejected: one partner atom per un-unrolled iteration, which makes ptxas emit 8-long runs
+// of DFMAs sharing the partner operand — full-rate register-file pattern — but costs more in loop
+// overhead and exposed LDS latency than it gains: 8.03 vs 7.37 ms on C1.)
 // ---- TMA bulk copy + mbarrier (sm_90+/sm_100a) ------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
