@@ -130,6 +130,18 @@ int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long num_pairs);
  * Defaults: everything. */
 int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1);
 
+/* Fused distance pass + hit broadcast (multi-GPU, one process per GPU).  Instead of all-gathering the
+ * per-pair hit bytes after the scan (what replaced the reference's MPI_Reduce, master.cpp:288), the
+ * scan kernel stores every hit directly into the hit buffer of EVERY rank through peer pointers
+ * over NVLink/NVSwitch (CUDA IPC); the only per-step collective left is a barrier between the scan
+ * and the accumulate pass.  Protocol: after each pair-list (re)build every rank calls
+ * edmd_peer_hits_export (two 64-byte IPC handles), the ranks exchange them, call
+ * edmd_peer_hits_open with all world x 2 handles and then synchronise once.  The two buffers
+ * alternate by step; each rank re-zeroes the one it has just consumed. */
+int edmd_peer_hits_export(edmd_engine* e, unsigned char* handles /* 128 bytes */);
+int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* world*128 bytes */, int world, int rank);
+int edmd_peer_hits_close(edmd_engine* e);
+
 /* ---- the five EDMD methods, batched over all (owned) tetrads ---------------------------- */
 /* EDMD::calculate_ED_Forces (edmd.cpp:64-166) incl. CalcRMSDRotationalMatrix
  * (qcprot.c:392-407).  Overwrites coordinates with the re-embedded ones, like the reference. */

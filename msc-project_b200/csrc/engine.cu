@@ -101,6 +101,15 @@ struct edmd_engine {
     void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0; long long partners_cap = 0;
     int pair_builder = 0;   // 0 auto, 1 sweep (reference O(n^2)), 2 cell list
 
+    // peer-shared hit flags (fused scan + broadcast over NVLink): two buffers used by step parity,
+    // exported with CUDA IPC; peer_tbl[b][r] = rank r's buffer b as mapped into this process
+    unsigned char* d_hitx[2] = {nullptr, nullptr};
+    long long hitx_cap = 0;
+    unsigned char** d_peer_tbl = nullptr;   // device array [2][world]
+    std::vector<void*> peer_opened;
+    int world = 1, rank_id = 0, hit_parity = 0;
+    bool peer_mode = false;
+
     // merge
     int* d_bp_off = nullptr;
     bool have_bp = false;
@@ -159,8 +168,11 @@ void timer_fold(edmd_engine* e, int id) {
 }
 
 void drop_graph(edmd_engine* e);
+void close_peers(edmd_engine* e);
 void free_system(edmd_engine* e) {
     drop_graph(e);
+    close_peers(e);
+    cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
     cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
     cudaFree(e->d_order); e->d_order = nullptr;
@@ -206,6 +218,7 @@ struct PtrKeyHash {
 };
 
 int ensure_pair_capacity(edmd_engine* e, long long np) {
+    close_peers(e);   // the driver re-establishes the peer-shared hit buffers after every rebuild
     if (np <= e->pairs_cap) return 0;
     long long cap = std::max(np, e->pairs_cap * 3 / 2 + 1024);
     cudaFree(e->d_pairs); cudaFree(e->d_hit);
@@ -256,6 +269,15 @@ int check_ready(edmd_engine* e, bool need_pairs) {
     return 0;
 }
 
+void close_peers(edmd_engine* e) {
+    for (void* p : e->peer_opened) cudaIpcCloseMemHandle(p);
+    e->peer_opened.clear();
+    cudaFree(e->d_peer_tbl); e->d_peer_tbl = nullptr;
+    e->peer_mode = false;
+}
+
+unsigned char* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx[e->hit_parity] : e->d_hit; }
+
 void drop_graph(edmd_engine* e) {
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
@@ -296,8 +318,9 @@ int do_ed(edmd_engine* e) {
 }
 int do_scan(edmd_engine* e) {
     timer_begin(e, T_SCAN);
-    CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, e->d_hit, e->p0, e->p1, e->S,
-                      nb_effective_cut2(e->sp), e->scan_mode, e->sms, e->st));
+    CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->S,
+                      nb_effective_cut2(e->sp), e->scan_mode, e->sms,
+                      e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
     timer_end(e, T_SCAN, e->p1 > e->p0 ? 1 : 0);
     e->hits_valid = true;
     return 0;
@@ -305,7 +328,7 @@ int do_scan(edmd_engine* e) {
 int do_accumulate(edmd_engine* e, int use_hits) {
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)e->n, e->st));
     timer_begin(e, T_ACC);
-    CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_adj_off,
+    CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_adj_off,
                             e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
                             e->sp, use_hits, e->nb_clip, e->st));
     timer_end(e, T_ACC, 1);
@@ -321,11 +344,15 @@ int do_finish(edmd_engine* e) {
         return do_integrate(e, 1, 1);
     }
     timer_begin(e, T_ACC);
-    CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, e->d_hit, e->d_pairs, e->np, e->d_adj_off,
+    CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
                               e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
                               e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n, e->t0,
                               e->t1 - e->t0, e->S, e->sp, e->st));
     timer_end(e, T_ACC, 3);
+    if (e->peer_mode) {   // this buffer is written again by the peers' scans two steps from now
+        CK(cudaMemsetAsync(e->d_hitx[e->hit_parity], 0, (size_t)e->np, e->st));
+        e->hit_parity ^= 1;
+    }
     e->latest_in_crd2 = true;
     return 0;
 }
@@ -1025,7 +1052,7 @@ int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes) {
         case EDMD_BUF_FED: p = e->fed; b = planes; break;
         case EDMD_BUF_RND: p = e->rnd; b = planes; break;
         case EDMD_BUF_FNB: p = e->fnb; b = planes; break;
-        case EDMD_BUF_HIT: p = e->d_hit; b = (size_t)e->np; break;
+        case EDMD_BUF_HIT: p = cur_hits(e); b = (size_t)e->np; break;
         case EDMD_BUF_CENTROID: p = e->cen; b = sizeof(double) * 4 * (size_t)e->n; break;
         default: return fail(EDMD_ERR_ARG, "unknown buffer %d", which);
     }
@@ -1101,7 +1128,7 @@ int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs) {
     CK(cudaSetDevice(e->device));
     std::vector<unsigned char> h((size_t)e->np);
     CK(cudaStreamSynchronize(e->st));
-    if (e->np) CK(cudaMemcpy(h.data(), e->d_hit, (size_t)e->np, cudaMemcpyDeviceToHost));
+    if (e->np) CK(cudaMemcpy(h.data(), cur_hits(e), (size_t)e->np, cudaMemcpyDeviceToHost));
     long long c = 0;
     for (long long p = e->p0; p < e->p1; p++) c += h[p] != 0;
     if (flagged_pairs) *flagged_pairs = c;
@@ -1114,6 +1141,61 @@ void* edmd_alloc_pinned(size_t bytes) {
     return p;
 }
 void edmd_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int edmd_peer_hits_export(edmd_engine* e, unsigned char* handles /* 2 x 64 bytes */) {
+    if (int rc = check_ready(e, true)) return rc;
+    if (!handles) return fail(EDMD_ERR_ARG, "null handle buffer");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->st));
+    close_peers(e);
+    const long long need = std::max<long long>(e->np, 1);
+    if (need > e->hitx_cap) {
+        cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
+        const long long cap = need + need / 2 + 4096;
+        CK(cudaMalloc((void**)&e->d_hitx[0], (size_t)cap)); CK(cudaMalloc((void**)&e->d_hitx[1], (size_t)cap));
+        e->hitx_cap = cap;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMemset(e->d_hitx[b], 0, (size_t)e->hitx_cap));
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, e->d_hitx[b]));
+        memcpy(handles + 64 * b, &h, 64);
+    }
+    return 0;
+}
+
+int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* world x 2 x 64 */, int world, int rank) {
+    if (int rc = check_ready(e, true)) return rc;
+    if (!all_handles || world < 1 || world > 32 || rank < 0 || rank >= world || !e->d_hitx[0])
+        return fail(EDMD_ERR_ARG, "edmd_peer_hits_open: bad arguments (export first; world <= 32)");
+    CK(cudaSetDevice(e->device));
+    close_peers(e);
+    std::vector<unsigned char*> tbl(2 * (size_t)world, nullptr);
+    for (int r = 0; r < world; r++)
+        for (int b = 0; b < 2; b++) {
+            if (r == rank) { tbl[(size_t)b * world + r] = e->d_hitx[b]; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all_handles + ((size_t)r * 2 + b) * 64, 64);
+            void* p = nullptr;
+            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            e->peer_opened.push_back(p);
+            tbl[(size_t)b * world + r] = (unsigned char*)p;
+        }
+    CK(cudaMalloc((void**)&e->d_peer_tbl, sizeof(unsigned char*) * tbl.size()));
+    CK(cudaMemcpy(e->d_peer_tbl, tbl.data(), sizeof(unsigned char*) * tbl.size(), cudaMemcpyHostToDevice));
+    e->world = world; e->rank_id = rank; e->hit_parity = 0; e->peer_mode = true;
+    drop_graph(e);
+    return 0;
+}
+
+int edmd_peer_hits_close(edmd_engine* e) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->st));
+    close_peers(e);
+    return 0;
+}
 
 int edmd_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
     int count = 0;

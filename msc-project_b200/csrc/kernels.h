@@ -19,7 +19,8 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
                              cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
-                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms, cudaStream_t st);
+                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
+                           unsigned char* const* peers, int world, cudaStream_t st);
 
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,

@@ -46,7 +46,16 @@ struct ScanArgs {
     int hi_cut;             // high word of the effective squared cutoff (MODE 0)
     int chunk;              // pairs per CTA
     double cut;             // effective squared cutoff (MODE 1)
+    // Fused compute + collective: when `peers` is set, a hit is stored straight into the hit buffer of
+    // EVERY rank (peer pointers over NVLink/NVSwitch, CUDA IPC) instead of being all-gathered later.
+    unsigned char* const* peers;   // [world] device pointers, this rank's own buffer included
+    int world;
 };
+
+__device__ __forceinline__ void publish_hit(const ScanArgs& A, long long k, int lane) {
+    if (A.peers) { if (lane < A.world) A.peers[lane][k] = 1; }
+    else if (lane == 0) A.hit[k] = 1;
+}
 
 constexpr int kScanThreads = 32;                       // one warp = one CTA = one tetrad pair at a time
 constexpr int kTI = kMaxStride / kScanThreads;         // 8 register-resident atoms per thread
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
         } else {
             pred = min(mm[0], mm[1]) <= A.hi_cut;
         }
-        if (__any_sync(0xffffffffu, pred) && lane == 0) A.hit[k] = 1;   // (also the WAR fence of the single buffer)
+        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);   // (the vote is also the WAR fence of the single buffer)
         pr = pr_next;
     }
 }
@@ -351,16 +360,19 @@ __global__ void __launch_bounds__(kScanThreads, 16) nb_scan32_kernel(ScanArgs A)
         bool pred = wild;
 #pragma unroll
         for (int r = 0; r < kTI; r++) pred = pred || (mm[r] <= hthr[r]);
-        if (__any_sync(0xffffffffu, pred) && lane == 0) A.hit[k] = 1;
+        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);
         pr = pr_next;
     }
 }
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
-                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms, cudaStream_t st) {
+                           long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
+                           unsigned char* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
-    if (err != cudaSuccess) return err;
+    if (!peers) {   // (peer mode: the buffers are zeroed by the double-buffer protocol in engine.cu)
+        cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
+        if (err != cudaSuccess) return err;
+    }
     const long long want = p1 - p0;
     long long chunk = want / ((long long)sms * 64);      // >= 64 chunks per SM when there is enough work
     if (chunk < 1) chunk = 1;
@@ -369,7 +381,7 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
     // hi-word test: r^2 < cut  ==>  hi(r^2) <= hi(cut); a superset, re-checked exactly later.
     long long bits; memcpy(&bits, &cut2_eff, 8);
     const bool gram = (mode >= 1) && cut2_eff >= 1e-3 && cut2_eff < 1e6;
-    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)chunk, cut2_eff};
+    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)chunk, cut2_eff, peers, world};
     const bool f32 = (mode == 2) && cut2_eff >= 1e-3 && cut2_eff <= 100.0;
     if (f32)       nb_scan32_kernel<<<grid, kScanThreads, 0, st>>>(A);
     else if (gram || mode == 2) nb_scan_kernel<1><<<grid, kScanThreads, 0, st>>>(A);

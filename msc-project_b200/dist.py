@@ -167,6 +167,8 @@ class EngineBackend:
     def merge(self): self.e.merge()
     def build_pairlist(self): return self.e.build_pairlist()
     def get_pairlist(self): return self.e.get_pairlist()
+    def peer_hits_export(self): return self.e.peer_hits_export()
+    def peer_hits_open(self, handles, world, rank): self.e.peer_hits_open(handles, world, rank)
     def sync(self): self.e.sync()
 
 
@@ -180,12 +182,16 @@ class ShardedEngine:
     """Runs the reference step protocol (simulation.cpp:34-55) over world_size ranks."""
 
     def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None, replicate=None,
-                 halo=None):
+                 halo=None, peer_hits=None):
         self.b, self.dist, self.n, self.rank, self.world, self.group = backend, dist, n_tetrads, rank, world, group
         self.replicate = (n_tetrads <= REPLICATE_MAX_TETRADS) if replicate is None else bool(replicate)
         # halo: sparse exchange of the tetrad blocks actually read (default for large systems)
         self.halo = (not self.replicate) if halo is None else (bool(halo) and not self.replicate)
         self.halo_plan = None
+        # fused scan + hit broadcast over peer memory (needs a backend with CUDA IPC: the GPU engine)
+        self.peer_hits = (hasattr(backend, "peer_hits_export") and world > 1) if peer_hits is None else bool(peer_hits)
+        self._peer_on = False
+        self._token = None
         self.plan = None
         self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
 
@@ -230,6 +236,11 @@ class ShardedEngine:
         self._all_gather_blocks(self.b.vel_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
 
     def gather_hits(self):
+        if self._peer_on:
+            # the scan kernel has already stored its hits into every rank's buffer over NVLink;
+            # what is left of the collective is the barrier before anyone reads them
+            self.dist.all_reduce(self._token, group=self.group)
+            return
         self._all_gather_blocks(self.b.hit_tensor(), 1, self.plan.np, self.plan.p_chunk)
 
     @property
@@ -256,6 +267,19 @@ class ShardedEngine:
             import torch
             with self.b.stream_ctx():
                 self.halo_plan = hp.exchange_lists(self.dist, torch, dev, self.group)
+        self._peer_on = False
+        if self.peer_hits and self.world > 1 and npairs > 0:
+            mine = self.b.peer_hits_export()
+            every = [None] * self.world
+            self.dist.all_gather_object(every, mine, group=self.group)
+            self.b.peer_hits_open(b"".join(every), self.world, self.rank)
+            if self._token is None:
+                import torch
+                self._token = torch.zeros(1, dtype=torch.int32, device=self.b.crd_tensor().device)
+            self.dist.barrier(group=self.group)     # every rank's buffers are zeroed and mapped
+            self._peer_on = True
+            if hasattr(self.b, "invalidate"):
+                self.b.invalidate()
         return npairs
 
     def set_rng(self, time0, rank, calls):

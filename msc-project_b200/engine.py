@@ -85,6 +85,9 @@ def load_library():
         "edmd_get_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
         "edmd_set_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
         "edmd_set_shard": (C.c_int, [E, C.c_int, C.c_int, LL, LL]),
+        "edmd_peer_hits_export": (C.c_int, [E, C.c_char_p]),
+        "edmd_peer_hits_open": (C.c_int, [E, C.c_char_p, C.c_int, C.c_int]),
+        "edmd_peer_hits_close": (C.c_int, [E]),
         "edmd_ed_forces": (C.c_int, [E]),
         "edmd_random_terms": (C.c_int, [E, C.c_int, C.c_long, C.c_int, C.c_long]),
         "edmd_nb_forces": (C.c_int, [E]),
@@ -333,6 +336,17 @@ class Engine:
 
     def set_nb_scan_mode(self, mode: int):
         self._ck(self.lib.edmd_set_nb_scan_mode(self.h, mode))
+
+    def peer_hits_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.lib.edmd_peer_hits_export(self.h, buf))
+        return buf.raw
+
+    def peer_hits_open(self, all_handles: bytes, world: int, rank: int):
+        self._ck(self.lib.edmd_peer_hits_open(self.h, all_handles, world, rank))
+
+    def peer_hits_close(self):
+        self._ck(self.lib.edmd_peer_hits_close(self.h))
 
     def ed_forces(self):
         self._ck(self.lib.edmd_ed_forces(self.h))
