@@ -573,16 +573,34 @@ __global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I,
     integrate_tetrad(I, t, zero, red);
 }
 
+// Persistent: a few CTAs sweep the mark bytes 256 at a time (marked tetrads are rare, an early-exit
+// CTA per tetrad would cost more than the sweep) and process the marked ones.
 __global__ void __launch_bounds__(kThreads, 2) finish_marked_kernel(AccArgs A, IntArgs I, const unsigned char* mark,
-                                                                  unsigned char* dirty) {
+                                                                  unsigned char* dirty, int count) {
     __shared__ AccSmem sm;
     __shared__ double red[1][kWarps];
-    const int t = A.t0 + blockIdx.x;
-    if (!mark[t]) return;
-    double f[3];
-    nb_accumulate_tetrad(A, t, sm, f);
-    if (threadIdx.x == 0) dirty[t] = 1;
-    integrate_tetrad(I, t, f, red);
+    __shared__ unsigned sMarks;
+    const int tid = threadIdx.x;
+    for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {   // 32-tetrad windows
+        if (tid < 32) {
+            const int e = base + tid;
+            const unsigned bal = __ballot_sync(0xffffffffu, e < count && mark[A.t0 + e] != 0);
+            if (tid == 0) sMarks = bal;
+        }
+        __syncthreads();
+        unsigned f = sMarks;
+        __syncthreads();
+        while (f) {
+            const int b = __ffs(f) - 1;
+            f &= f - 1;
+            const int t = A.t0 + base + b;
+            double fr[3];
+            nb_accumulate_tetrad(A, t, sm, fr);
+            if (tid == 0) dirty[t] = 1;
+            integrate_tetrad(I, t, fr, red);
+            __syncthreads();
+        }
+    }
 }
 
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
@@ -604,7 +622,9 @@ cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, cons
               cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1, 1};
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
     finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
-    finish_marked_kernel<<<count, kThreads, 0, st>>>(A, I, mark, dirty);
+    int sweep = (count + 31) / 32;
+    if (sweep > 148 * 2) sweep = 148 * 2;
+    finish_marked_kernel<<<sweep, kThreads, 0, st>>>(A, I, mark, dirty, count);
     return cudaGetLastError();
 }
 
