@@ -83,8 +83,10 @@ int  edmd_set_nb_clip(edmd_engine* e, int on);
 /* Arithmetic form of the NB distance pass (nb_scan_kernel): 0 = direct differences exactly
  * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (default; 4 instead of
  * 6 FP64 instructions per atom pair), 2 = the same test in FP32 with packed FFMA2 and a proven
- * error margin (the "FP32 variant" of BASELINE configs[4]).  The pass only selects tetrad pairs
- * for the exact FP64 force kernel, so forces and energies are bit-identical in all modes. */
+ * error margin (the "FP32 variant" of BASELINE configs[4]), 4 = form 1 plus bounding-sphere culling of
+ * whole pairs and of 32 x 32 atom blocks (no longer the reference's brute-force work: opt-in).  The pass
+ * only selects tetrad pairs for the exact FP64 force kernel, so forces and energies are bit-identical
+ * in all modes. */
 int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
 
 /* ---- data in / out ----------------------------------------------------------------- */

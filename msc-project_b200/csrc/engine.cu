@@ -78,7 +78,10 @@ struct edmd_engine {
     double* crd2 = nullptr;        // post-integrate coordinates written by the fused finish kernel
     bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
-    unsigned char *d_mark = nullptr, *d_dirty = nullptr;   // per-tetrad: in a flagged pair now / fnb non-zero
+    unsigned char *d_mark = nullptr, *d_dirty = nullptr;
+    double* d_gb = nullptr;                 // [n][8][4] group bounding spheres (scan mode 4)
+    unsigned long long* d_pmask = nullptr;  // [pairs_cap] 8x8 group masks per pair (scan mode 4)
+    long long pmask_cap = 0;   // per-tetrad: in a flagged pair now / fnb non-zero
     bool rnd_zero = true;   // random terms currently all zero
 
     // staging (interleaved flat), 3 slots
@@ -175,6 +178,7 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
     cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
+    cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -221,10 +225,12 @@ int ensure_pair_capacity(edmd_engine* e, long long np) {
     close_peers(e);   // the driver re-establishes the peer-shared hit buffers after every rebuild
     if (np <= e->pairs_cap) return 0;
     long long cap = std::max(np, e->pairs_cap * 3 / 2 + 1024);
-    cudaFree(e->d_pairs); cudaFree(e->d_hit);
-    e->d_pairs = nullptr; e->d_hit = nullptr; e->pairs_cap = 0;
+    cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_pmask);
+    e->d_pairs = nullptr; e->d_hit = nullptr; e->d_pmask = nullptr; e->pairs_cap = 0; e->pmask_cap = 0;
     CK(dev_alloc(&e->d_pairs, (size_t)cap));
     CK(dev_alloc(&e->d_hit, (size_t)cap));
+    CK(dev_alloc(&e->d_pmask, (size_t)cap));
+    e->pmask_cap = cap;
     e->pairs_cap = cap;
     return 0;
 }
@@ -317,6 +323,16 @@ int do_ed(edmd_engine* e) {
     return 0;
 }
 int do_scan(edmd_engine* e) {
+    const double cut_eff = nb_effective_cut2(e->sp);
+    if (e->scan_mode == 4 && cut_eff >= 1e-3 && cut_eff < 1e6) {
+        timer_begin(e, T_SCAN);
+        CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
+                               e->d_gb, e->d_pmask,
+                               e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
+        timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
+        e->hits_valid = true;
+        return 0;
+    }
     timer_begin(e, T_SCAN);
     CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->S,
                       nb_effective_cut2(e->sp), e->scan_mode, e->sms,
@@ -468,7 +484,7 @@ int edmd_set_nb_clip(edmd_engine* e, int on) {
 
 int edmd_set_nb_scan_mode(edmd_engine* e, int mode) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
-    if (mode < 0 || mode > 2) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram, 2 fp32 prefilter)", mode);
+    if (mode < 0 || mode > 4 || mode == 3) return fail(EDMD_ERR_ARG, "scan mode %d unknown (0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling)", mode);
     e->scan_mode = mode;
     drop_graph(e);
     return 0;
@@ -558,6 +574,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
     CK(dev_alloc(&e->d_mark, (size_t)n)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(dev_alloc(&e->d_gb, (size_t)n * 32));
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)n, e->st));   // unknown force contents: treat as dirty
     CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
     CK(dev_alloc(&e->d_stage, 3 * (size_t)e->total3));

@@ -55,10 +55,10 @@ def test_ragged_stochastic_trajectory(edmd, po, ragged):
 
 def test_both_scan_modes_give_identical_results(edmd, ragged):
     out = []
-    for mode in (0, 1, 2):
+    for mode in (0, 1, 2, 4):
         g = edmd.Engine(ragged); g.set_nb_scan_mode(mode); g.build_pairlist(); g.step(4)
         out.append(g.get_state() + (g.flagged_pairs(),))
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert np.array_equal(out[0][0], out[k][0]) and np.array_equal(out[0][1], out[k][1])
         assert out[k][2] >= out[0][2] >= 1           # filters are supersets of the direct FP64 test
 
