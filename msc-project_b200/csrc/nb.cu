@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
         // software-pipelined: operands of step j+2 are fetched before step j's arithmetic
         double2 xs = *reinterpret_cast<const double2*>(bx), ys = *reinterpret_cast<const double2*>(by);
         double2 zs = *reinterpret_cast<const double2*>(bz), ws = *reinterpret_cast<const double2*>(bw);
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < ns2; j += 2) {
             const double2 nxs = *reinterpret_cast<const double2*>(bx + j + 2);
             const double2 nys = *reinterpret_cast<const double2*>(by + j + 2);
