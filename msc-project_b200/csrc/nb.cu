@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kScanThreads, 16) nb_scan32_kernel(ScanArgs A)
         for (int r = 0; r < kTI; r++) mm[r] = 0x7fffffff;
         float4 xs = *reinterpret_cast<const float4*>(sb[0]), ys = *reinterpret_cast<const float4*>(sb[1]);
         float4 zs = *reinterpret_cast<const float4*>(sb[2]), ws = *reinterpret_cast<const float4*>(sb[3]);
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < ns4; j += 4) {
             const float4 nxs = *reinterpret_cast<const float4*>(sb[0] + j + 4);
             const float4 nys = *reinterpret_cast<const float4*>(sb[1] + j + 4);
