@@ -80,6 +80,7 @@ struct edmd_engine {
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     unsigned char *d_mark = nullptr, *d_dirty = nullptr;
     double* d_gb = nullptr;                 // [n][8][4] group bounding spheres (scan mode 4)
+    int* d_perm = nullptr;                  // [P][S] slot -> atom, compact groups of 32 (scan mode 4)
     unsigned long long* d_pmask = nullptr;  // [pairs_cap] 8x8 group masks per pair (scan mode 4)
     long long pmask_cap = 0;   // per-tetrad: in a flagged pair now / fnb non-zero
     bool rnd_zero = true;   // random terms currently all zero
@@ -178,6 +179,7 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
     cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
+    cudaFree(e->d_perm); e->d_perm = nullptr;
     cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
@@ -327,7 +329,7 @@ int do_scan(edmd_engine* e) {
     if (e->scan_mode == 4 && cut_eff >= 1e-3 && cut_eff < 1e6) {
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
-                               e->d_gb, e->d_pmask,
+                               e->d_gb, e->d_pmask, e->d_param_id, e->d_perm,
                                e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -564,6 +566,39 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
         }
     }
 
+    // slot permutation for the culling scan: recursive coordinate bisection of each average structure
+    // into 8 groups of <= 32 atoms (slots 32g..32g+31), padded with -1
+    std::vector<int> perm((size_t)P * S, -1);
+    for (int p = 0; p < P; p++) {
+        const edmd_tetrad& T = tets[rep[p]];
+        std::vector<int> idx(T.num_Atoms);
+        for (int a = 0; a < T.num_Atoms; a++) idx[a] = a;
+        // split [lo,hi) into `parts` groups along the longest axis, sizes as even as possible
+        struct Job { int lo, hi, parts, first; };
+        std::vector<Job> jobs{{0, T.num_Atoms, 8, 0}};
+        while (!jobs.empty()) {
+            Job j = jobs.back(); jobs.pop_back();
+            if (j.parts == 1) {
+                for (int q = j.lo; q < j.hi && q - j.lo < 32; q++) perm[(size_t)p * S + 32 * j.first + (q - j.lo)] = idx[q];
+                continue;
+            }
+            double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+            for (int q = j.lo; q < j.hi; q++)
+                for (int c = 0; c < 3; c++) { const double v = T.avg[3 * idx[q] + c]; mn[c] = std::min(mn[c], v); mx[c] = std::max(mx[c], v); }
+            int ax = 0;
+            for (int c = 1; c < 3; c++) if (mx[c] - mn[c] > mx[ax] - mn[ax]) ax = c;
+            std::sort(idx.begin() + j.lo, idx.begin() + j.hi, [&](int a, int b) { return T.avg[3 * a + ax] < T.avg[3 * b + ax]; });
+            const int half = j.parts / 2;
+            int cnt = j.hi - j.lo;
+            int left = (cnt + 1) / 2;
+            if (left > 32 * half) left = 32 * half;
+            if (cnt - left > 32 * half) left = cnt - 32 * half;
+            jobs.push_back({j.lo, j.lo + left, half, j.first});
+            jobs.push_back({j.lo + left, j.hi, half, j.first + half});
+        }
+    }
+    CK(dev_alloc(&e->d_perm, perm.size()));
+    CK(cudaMemcpyAsync(e->d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, e->st));
     CK(dev_alloc(&e->d_natoms, n)); CK(dev_alloc(&e->d_param_id, n)); CK(dev_alloc(&e->d_off3, n + 1));
     CK(dev_alloc(&e->d_ps_na, P)); CK(dev_alloc(&e->d_ps_nev, P));
     CK(dev_alloc(&e->d_avg, avg.size())); CK(dev_alloc(&e->d_mass, mass.size())); CK(dev_alloc(&e->d_chg, chg.size()));

@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 }
 
 // ---- MODE 4: gram form + bounding-sphere culling ---------------------------------------------------
-// Atoms 32g .. 32g+31 of a tetrad form group g (8 groups; in the register tile group r is exactly
-// register r).  group_bounds_kernel gives every group a bounding sphere; pair_masks_kernel turns the
+// The 256 slots of a tetrad are filled with its atoms through a per-parameter-set permutation that
+// makes slots 32g .. 32g+31 a spatially compact group g (recursive coordinate bisection of the average
+// structure, engine.cu); in the register tile group r is exactly register r.  group_bounds_kernel gives every group a bounding sphere; pair_masks_kernel turns the
 // 8 x 8 sphere tests of a tetrad pair into a 64-bit mask (bit 8g + r: register group r may be within
 // sqrt(cut) of partner group g); the scan then skips whole pairs (mask 0: no TMA, no staging) and,
 // inside a pair, every (register group, partner group) block whose spheres are too far apart.
@@ -262,15 +263,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 // selected pairs remain a superset of the true hits and the final forces are bit-identical.
 // Work is no longer the reference's 63,504 atom pairs per listed pair — this mode is opt-in
 // (edmd_set_nb_scan_mode(4)) and reported separately from the brute-force headline.
-__global__ void group_bounds_kernel(const double* crd, const int* natoms, double* gb, int n, int S) {
+__global__ void group_bounds_kernel(const double* crd, const int* natoms, const int* param_id, const int* perm,
+                                    double* gb, int n, int S) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
     const double* X = crd + (size_t)t * 3 * S;
-    const int na = natoms[t];
+    const int* PM = perm + (size_t)param_id[t] * S;
     for (int g = 0; g < 8; g++) {
-        const int a = 32 * g + lane;
-        const bool on = a < na;
+        const int a = PM[32 * g + lane];      // slot -> atom (spatially compact groups), -1 = empty slot
+        const bool on = a >= 0;
         double x = on ? X[a] : 0.0, y = on ? X[S + a] : 0.0, z = on ? X[2 * S + a] : 0.0;
         double sx = x, sy = y, sz = z; int cnt = on ? 1 : 0;
 #pragma unroll
@@ -319,7 +321,8 @@ __global__ void pair_masks_kernel(const double* gb, const int2* pairs, long long
     mask[k] = m;
 }
 
-__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_kernel(ScanArgs A, const unsigned long long* mask) {
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_kernel(ScanArgs A, const unsigned long long* mask,
+                                                                                    const int* param_id, const int* perm) {
     constexpr double kBias = 16384.0;
     __shared__ __align__(16) double sb[4][kMaxStride + 2];
     __shared__ __align__(128) double raw[3 * kMaxStride];
@@ -354,16 +357,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
         int2 pr_next = pr;
         if (kn < k1) pr_next = A.pairs[kn];
         const int tr = pr.x < pr.y ? pr.x : pr.y;
-        const int ns = A.natoms[pr.x < pr.y ? pr.y : pr.x];
+        const int tsc = pr.x < pr.y ? pr.y : pr.x;
         if (tr != cur_r) {
             cur_r = tr;
             const double* Xr = A.crd + (size_t)tr * 3 * S;
-            const int nr = A.natoms[tr];
+            const int* PR = perm + (size_t)param_id[tr] * S;
             ox = Xr[0]; oy = Xr[S]; oz = Xr[2 * S]; wild = false;
 #pragma unroll
             for (int r = 0; r < kTI; r++) {
-                const int a = lane + kScanThreads * r;
-                if (a < nr) {
+                const int a = PR[lane + kScanThreads * r];     // slot -> atom
+                if (a >= 0) {
                     const double lx = Xr[a] - ox, ly = Xr[S + a] - oy, lz = Xr[2 * S + a] - oz;
                     xi[r] = -2.0 * lx; yi[r] = -2.0 * ly; zi[r] = -2.0 * lz;
                     const double w = fma(lz, lz, fma(ly, ly, lx * lx));
@@ -374,15 +377,16 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
         }
         mbar_wait(&bar, phase);
         phase ^= 1;
-        const int ns2 = (ns + 1) & ~1;
+        {   // stage all 256 slots of the partner in its own compact-group order (empty slots never hit)
+            const int* PS = perm + (size_t)param_id[tsc] * S;
 #pragma unroll
-        for (int r = 0; r < kTI; r++) {
-            const int a = lane + kScanThreads * r;
-            if (a < ns2) {
-                const bool real = a < ns;
-                const double lx = raw[a] - ox, ly = raw[S + a] - oy, lz = raw[2 * S + a] - oz;
-                sb[0][a] = real ? lx : 0.0; sb[1][a] = real ? ly : 0.0; sb[2][a] = real ? lz : 0.0;
-                sb[3][a] = real ? fma(lz, lz, fma(ly, ly, lx * lx)) + kBias : 1e300;
+            for (int r = 0; r < kTI; r++) {
+                const int slot = lane + kScanThreads * r;
+                const int a = PS[slot];
+                const bool real = a >= 0;
+                const double lx = real ? raw[a] - ox : 0.0, ly = real ? raw[S + a] - oy : 0.0, lz = real ? raw[2 * S + a] - oz : 0.0;
+                sb[0][slot] = lx; sb[1][slot] = ly; sb[2][slot] = lz;
+                sb[3][slot] = real ? fma(lz, lz, fma(ly, ly, lx * lx)) + kBias : 1e300;
             }
         }
         __syncwarp();
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
         for (int g = 0; g < 8; g++) {
             const unsigned m8 = (unsigned)(m >> (8 * g)) & 0xffu;
             if (!m8) continue;
-            const int jhi = (32 * g + 32 < ns2) ? 32 * g + 32 : ns2;
+            const int jhi = 32 * g + 32;
 #pragma unroll 2
             for (int j = 32 * g; j < jhi; j += 2) {
                 const double2 xs = *reinterpret_cast<const double2*>(sb[0] + j);
@@ -426,13 +430,14 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* mask, unsigned char* const* peers, int world, cudaStream_t st) {
+                                unsigned long long* mask, const int* param_id, const int* perm,
+                                unsigned char* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
-    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, gb, n, S);
+    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S);
     const long long want = p1 - p0;
     pair_masks_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), mask);
     long long chunk = want / ((long long)sms * 64);
@@ -441,7 +446,7 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     const int grid = (int)((want + chunk - 1) / chunk);
     long long bits; memcpy(&bits, &cut2_eff, 8);
     ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)chunk, cut2_eff, peers, world};
-    nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, mask);
+    nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, mask, param_id, perm);
     return cudaGetLastError();
 }
 
