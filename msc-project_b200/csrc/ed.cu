@@ -24,6 +24,7 @@
 //    reference walks it twice, the second time with stride 3N, edmd.cpp:106-127).
 //    Roofline: HBM — 96,872 algorithmic bytes per tetrad (SURVEY.md §8a a-ED); with
 //    de-duplicated parameter sets resident in L2 the DRAM traffic drops to the 24 KB of state.
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -464,6 +465,142 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
     }
 }
 
+// ---- warp-per-tetrad projection (parameter sets with <= kNevReg eigenvectors) -----------------------
+// The CTA stages the parameter set's eigenvectors [12][3][S] and average structure [3][S] in shared
+// memory once per run of tetrads that share the set (`order` is sorted by set); after that every
+// warp projects its own tetrads with no CTA barrier: lane l owns atoms l, l+32, ... (8 per lane),
+// the twelve partial projections are summed with the halving butterfly and handed back to all lanes
+// with shuffles.  ~2,000 warp instructions per tetrad against ~6,800 for the thread-per-atom kernel
+// (whose eight warps each run the butterfly and then meet at two barriers per tetrad).
+// Bound: shared-memory bandwidth, 2 passes x 36 coefficients x 256 atoms x 8 B = 147 KB per tetrad.
+__device__ __forceinline__ constexpr int reduce12_owner(int j) {   // inverse of reduce12_index (even lane)
+    return 16 * (j / 6) + 8 * ((j % 6) / 3) + ((j % 3) == 2 ? 4 : 0) + ((j % 3) == 1 ? 2 : 0);
+}
+
+__global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) {
+    extern __shared__ double wsm[];
+    __shared__ int sNext;
+    const int S = A.ps.S;
+    double* sEV = wsm;               // [kNevReg][3][S]
+    double* sAV = wsm + kNevReg * 3 * S;   // [3][S]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e0 = blockIdx.x * A.chunk;
+    const int e1 = (e0 + A.chunk < A.count) ? e0 + A.chunk : A.count;
+    const int nk = S >> 5;
+    const int my_idx = reduce12_index(lane);
+
+    int base = e0;
+    while (base < e1) {
+        const int ps = A.param_id[A.order[base]];
+        const int na = A.ps.na[ps], nev = A.ps.nev[ps];
+        if (tid == 0) sNext = e1;
+        {   // stage the set's tables (rows j >= NEV are zero; the arrays are zero-padded beyond na / nev)
+            const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
+            const double* AV = A.ps.avg + (size_t)ps * 3 * S;
+            const int have = A.ps.NEV * 3 * S;
+            for (int i = tid; i < kNevReg * 3 * S; i += kThreads) sEV[i] = i < have ? EV[i] : 0.0;
+            for (int i = tid; i < 3 * S; i += kThreads) sAV[i] = AV[i];
+        }
+        __syncthreads();
+        double el = 1.0;
+        if (my_idx >= 0 && my_idx < nev) el = A.ps.eval[(size_t)ps * A.ps.NEV + my_idx];
+
+        int e = base + warp;
+        int t = e < e1 ? A.order[e] : -1;
+        while (e < e1) {
+            if (A.param_id[t] != ps) break;
+            const int e_next = e + kWarps;
+            const int t_next = e_next < e1 ? A.order[e_next] : -1;
+            const double* XIN = A.crd_in + (size_t)t * 3 * S;
+            const double* SUP = A.sup + (size_t)t * kSupWords;
+            double x[8][3];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int a = lane + 32 * k;
+                x[k][0] = x[k][1] = x[k][2] = 0.0;
+                if (k < nk && a < na) { x[k][0] = XIN[a]; x[k][1] = XIN[S + a]; x[k][2] = XIN[2 * S + a]; }
+            }
+            double v[kNevReg];
+#pragma unroll
+            for (int j = 0; j < kNevReg; j++) v[j] = 0.0;
+            {
+                double R[9];
+#pragma unroll
+                for (int q = 0; q < 9; q++) R[q] = SUP[q];
+                const double ca0 = SUP[12], ca1 = SUP[13], ca2 = SUP[14];
+                const double cx0 = SUP[15], cx1 = SUP[16], cx2 = SUP[17];
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int a = lane + 32 * k;
+                    if (k < nk) {
+                        double d0 = 0, d1 = 0, d2 = 0;
+                        if (a < na) {   // edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
+                            const double ac0 = sAV[a] - ca0, ac1 = sAV[S + a] - ca1, ac2 = sAV[2 * S + a] - ca2;
+                            const double xc0 = x[k][0] - cx0, xc1 = x[k][1] - cx1, xc2 = x[k][2] - cx2;
+                            d0 = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
+                            d1 = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
+                            d2 = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
+                        }
+#pragma unroll
+                        for (int j = 0; j < kNevReg; j++) {   // edmd.cpp:106-110
+                            const double* c = sEV + (size_t)j * 3 * S + a;
+                            v[j] = fma(c[0], d0, fma(c[S], d1, fma(c[2 * S], d2, v[j])));
+                        }
+                    }
+                }
+            }
+            // warp totals; the lane that owns projection j derives the force weight and energy term
+            const double mine = warp_reduce12(v, lane);
+            const double pw_mine = mine * A.scaled / el;
+            const double en_mine = mine * mine / el;
+            double p[kNevReg], w[kNevReg];
+            double en = 0.0;
+#pragma unroll
+            for (int j = 0; j < kNevReg; j++) {
+                p[j] = __shfl_sync(0xffffffffu, mine, reduce12_owner(j));
+                w[j] = __shfl_sync(0xffffffffu, pw_mine, reduce12_owner(j));
+                const double q = __shfl_sync(0xffffffffu, en_mine, reduce12_owner(j));
+                if (j < nev) en += q;                          // edmd.cpp:153-157
+            }
+            if (lane == 0) A.e_ed[t] = en * (0.5 * A.scaled);
+
+            // re-embedding, force (edmd.cpp:113-127) and back to the laboratory frame (:130-150)
+            double R[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) R[q] = SUP[q];
+            const double shift0 = SUP[9], shift1 = SUP[10], shift2 = SUP[11];
+            double* X = A.crd + (size_t)t * 3 * S;
+            double* F = A.fed + (size_t)t * 3 * S;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int a = lane + 32 * k;
+                if (k < nk && a < na) {
+                    double s0 = sAV[a], s1 = sAV[S + a], s2 = sAV[2 * S + a], f0 = 0, f1 = 0, f2 = 0;
+#pragma unroll
+                    for (int j = 0; j < kNevReg; j++) {
+                        const double* c = sEV + (size_t)j * 3 * S + a;
+                        const double c0 = c[0], c1 = c[S], c2 = c[2 * S];
+                        s0 = fma(c0, p[j], s0); s1 = fma(c1, p[j], s1); s2 = fma(c2, p[j], s2);
+                        f0 = fma(-c0, w[j], f0); f1 = fma(-c1, w[j], f1); f2 = fma(-c2, w[j], f2);
+                    }
+                    s0 -= shift0; s1 -= shift1; s2 -= shift2;
+                    X[a]         = R[0] * s0 + R[3] * s1 + R[6] * s2;
+                    X[S + a]     = R[1] * s0 + R[4] * s1 + R[7] * s2;
+                    X[2 * S + a] = R[2] * s0 + R[5] * s1 + R[8] * s2;
+                    F[a]         = R[0] * f0 + R[3] * f1 + R[6] * f2;
+                    F[S + a]     = R[1] * f0 + R[4] * f1 + R[7] * f2;
+                    F[2 * S + a] = R[2] * f0 + R[5] * f1 + R[8] * f2;
+                }
+            }
+            e = e_next; t = t_next;
+        }
+        if (lane == 0 && e < e1) atomicMin(&sNext, e);   // first tetrad of the next set seen by this warp
+        __syncthreads();
+        base = sNext;
+        __syncthreads();
+    }
+}
+
 cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                              cudaStream_t st) {
@@ -472,6 +609,22 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
     superpose_kernel<<<(count + 1) / 2, kSupThreads, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
+    static const bool force_cta = getenv("EDMD_ED_CTA") != nullptr;   // A/B switch for tools/probe_perf.py
+    if (ps.NEV <= kNevReg && !force_cta) {
+        const size_t smem = sizeof(double) * (kNevReg * 3 + 3) * ps.S;
+        static bool configured = false;
+        if (!configured) {
+            err = cudaFuncSetAttribute(ed_project_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(sizeof(double) * (kNevReg * 3 + 3) * kMaxStride));
+            if (err != cudaSuccess) return err;
+            configured = true;
+        }
+        int chunk = (count + 2 * sms - 1) / (2 * sms);   // two resident CTAs per SM, one wave
+        if (chunk < kWarps) chunk = kWarps;              // at least one tetrad per warp
+        EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
+        ed_project_warp_kernel<<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
+        return cudaGetLastError();
+    }
     int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer
     if (chunk < 1) chunk = 1;
     if (chunk > 8) chunk = 8;
