@@ -81,12 +81,13 @@ int  edmd_set_nb_consts(edmd_engine* e, double krep, double qfac);
  * class-EDMD shim to return raw pair forces. */
 int  edmd_set_nb_clip(edmd_engine* e, int on);
 /* Arithmetic form of the NB distance pass (nb_scan_kernel): 0 = direct differences exactly
- * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (default; 4 instead of
- * 6 FP64 instructions per atom pair), 2 = the same test in FP32 with packed FFMA2 and a proven
- * error margin (the "FP32 variant" of BASELINE configs[4]), 4 = form 1 plus bounding-sphere culling of
- * whole pairs and of 32 x 32 atom blocks (no longer the reference's brute-force work: opt-in).  The pass
- * only selects tetrad pairs for the exact FP64 force kernel, so forces and energies are bit-identical
- * in all modes. */
+ * as edmd.cpp:251-256, 1 = pair-local Gram form |xi|^2+|xj|^2-2xi.xj (3 instead of 6 FP64
+ * instructions per atom pair), 2 = the same test in FP32 with packed FFMA2 and a proven error
+ * margin (the "FP32 variant" of BASELINE configs[4]), 4 = form 1 plus exact bounding-sphere
+ * culling of whole tetrad pairs and of 32 x 32 atom blocks (default).  Modes 0-2 evaluate all
+ * 63,504 atom pairs of every listed tetrad pair like the reference does; mode 4 skips blocks that
+ * provably hold no atom pair inside the cutoff.  The pass only selects tetrad pairs for the exact
+ * FP64 force kernel, so forces and energies are bit-identical in all modes. */
 int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
 
 /* ---- data in / out ----------------------------------------------------------------- */
@@ -180,6 +181,11 @@ int edmd_get_energies(edmd_engine* e, double out[4]);
  * from the value passed to edmd_set_rng. */
 int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before);
 int edmd_step(edmd_engine* e, int nsteps, int random_mode);
+/* edmd_set_state + edmd_step + edmd_get_state in one call, in place on the caller's Tetrad
+ * array (Master's view of a step: host tetrads in, host tetrads out, master.cpp:268-343).  When
+ * the coordinate and velocity arrays are one slab each (edmd_alloc_pinned), the velocity upload
+ * overlaps the ED and distance kernels.  Same results as the three separate calls. */
+int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int random_mode);
 /* edmd_step replays a CUDA graph of one step (on by default; off: plain kernel launches). */
 int edmd_set_graph(edmd_engine* e, int on);
 int edmd_sync(edmd_engine* e);

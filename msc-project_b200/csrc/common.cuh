@@ -36,6 +36,7 @@ struct ParamSets {                // device pointers, de-duplicated static data
     const double* eval;           // [P][NEV]
     const double* evec;           // [P][NEV][3][S]
     int S, NEV;
+    const double* pre = nullptr;  // [P][4] centroid of avg + sum |avg_c|^2 (ed.cu: ps_precompute_kernel)
 };
 
 // Sum K doubles over the CTA; every thread returns with the totals in v[].

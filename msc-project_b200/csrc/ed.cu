@@ -5,25 +5,29 @@
 //
 // Two kernels per batch:
 //
-//  superpose_kernel (64 threads per tetrad, up to 10 tetrads resident per SM): centroids, 3x3
+//  superpose_kernel (one warp per tetrad, ~20 tetrads resident per SM): centroid, 3x3
 //    cross-covariance, QCP rotation and the offset vector.  The rotation feeds
 //    d = R*x_c - avg_c, a difference of ~10 A vectors that is ~0.1 A long, so last-bit
 //    differences of the sums are amplified ~100x into the forces.  To stay robustly inside the
-//    1e-10 parity bound (and usually at 1e-15) the 20 reductions are done in the reference's
+//    1e-10 parity bound (and usually at 1e-15) the reductions are done in the reference's
 //    SEQUENTIAL atom order (qcprot.c:370-379, 132-157; edmd.cpp:97-101): per-atom terms are
-//    produced in parallel into shared memory, then lane k of one warp runs the k-th running sum
-//    as a chain of 252 DADDs.  This file is compiled with -fmad=false, so every expression
-//    rounds exactly like the CPU build and R, centroids and offset are BIT-IDENTICAL to the
-//    reference's.  Latency-bound (3 x 252 dependent adds) and hidden by occupancy.
+//    produced 32 atoms at a time by the whole warp into a shared tile, then lane k runs the
+//    k-th running sum as a chain of DADDs.  The sums that depend only on the parameter set
+//    (centroid and norm of the average structure) are computed once at upload.  This file is
+//    compiled with -fmad=false, so every expression rounds exactly like the CPU build and R,
+//    centroids and offset are BIT-IDENTICAL to the reference's.  Latency-bound (3 x 252
+//    dependent adds per tetrad) and hidden by the ~20 independent warps per SM.
 //
-//  ed_project_kernel (256 threads per tetrad, thread a <-> atom a): displacement, projections
-//    on the eigenvectors (fixed-order CTA tree sums — the only place the summation order differs
-//    from the CPU, ~1e-16 relative), re-embedding, force, rotation back.  Each thread keeps its
-//    atom's 3 x nev eigenvector coefficients in registers between the projection pass and the
-//    re-embedding pass, so the 72.6 KB eigenvector block crosses the memory system once (the
-//    reference walks it twice, the second time with stride 3N, edmd.cpp:106-127).
+//  ed_project_warp_kernel (parameter sets with <= 12 eigenvectors: one warp per tetrad, the set's
+//    eigenvectors staged in shared memory once per run of tetrads) and ed_project_kernel (any
+//    number of eigenvectors: 256 threads per tetrad, thread a <-> atom a, coefficients in
+//    registers): displacement, projections on the eigenvectors (fixed-order tree sums — the only
+//    place the summation order differs from the CPU, ~1e-16 relative), re-embedding, force,
+//    rotation back.  The 72.6 KB eigenvector block crosses the memory system once per run (the
+//    reference walks it twice per tetrad, the second time with stride 3N, edmd.cpp:106-127).
 //    Roofline: HBM — 96,872 algorithmic bytes per tetrad (SURVEY.md §8a a-ED); with
-//    de-duplicated parameter sets resident in L2 the DRAM traffic drops to the 24 KB of state.
+//    de-duplicated parameter sets resident in L2 / shared memory the DRAM traffic drops to the
+//    24 KB of state.
 #include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
@@ -116,9 +120,10 @@ __device__ void qcp_rotation(double R[9], const double M[9], double e0) {
     R[6] = 2 * (ki + wj);     R[7] = 2 * (jk - wi);     R[8] = w2 - i2 - j2 + k2;
 }
 
-constexpr int kSupThreads = 128;                 // one CTA = TWO tetrads (64 threads each)
+constexpr int kSupWarps = 4;                      // one warp = one tetrad; no CTA-wide barrier anywhere
 constexpr int kSupWords = 24;   // per tetrad: R[9], shift[3], avg centroid[3], x centroid[3], pad
-constexpr int kSupRow = kMaxStride + 1;           // +1: lanes k = 0..10 hit distinct banks
+constexpr int kSupRow = kMaxStride + 1;
+constexpr int kTileRow = 33;                      // 32 atoms + 1: chain lanes k = 0..9 hit distinct banks
 
 struct SupArgs {
     ParamSets ps;
@@ -128,24 +133,8 @@ struct SupArgs {
     int t0, count;
 };
 
-// Running sum, in atom order and starting from 0.0, of  (p1*q1 + p2*q2) + p3*q3  over i < na.
-// With p2 = p3 = a row of zeros this is the plain product sum p1*q1 (adding +0.0 is exact), with
-// q = a row of ones and p2 = p3 = zeros the plain sum of p1.  8 elements' loads and products are
-// issued before their 8 dependent adds, so the chain runs at DADD latency.
-__device__ __forceinline__ double seq_sum3(const double* p1, const double* q1, const double* p2, const double* q2,
-                                           const double* p3, const double* q3, int na) {
-    double s = 0.0;
-    int i = 0;
-    for (; i + 8 <= na; i += 8) {
-        double v[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = (p1[i + u] * q1[i + u] + p2[i + u] * q2[i + u]) + p3[i + u] * q3[i + u];
-#pragma unroll
-        for (int u = 0; u < 8; u++) s = s + v[u];
-    }
-    for (; i < na; i++) s = s + ((p1[i] * q1[i] + p2[i] * q2[i]) + p3[i] * q3[i]);
-    return s;
-}
+// Running sum of p[0..na) in atom order, starting from 0.0 — the reference's `s += p[i]` loops.
+// Eight loads are issued before their eight dependent adds, so the chain runs at DADD latency.
 __device__ __forceinline__ double seq_sum1(const double* p, int na) {
     double s = 0.0;
     int i = 0;
@@ -157,104 +146,150 @@ __device__ __forceinline__ double seq_sum1(const double* p, int na) {
     for (; i < na; i++) s = s + p[i];
     return s;
 }
+// s += row[0..cnt) for one 32-atom tile row (cnt <= 32).
+__device__ __forceinline__ double tile_chain(double s, const double* row, int cnt) {
+    if (cnt == 32) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            double v[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = row[16 * h + u];
+#pragma unroll
+            for (int u = 0; u < 16; u++) s = s + v[u];
+        }
+    } else {
+        for (int i = 0; i < cnt; i++) s = s + row[i];
+    }
+    return s;
+}
 
-// Two tetrads per CTA: threads 0-63 serve tetrad A, 64-127 tetrad B (4 atoms each) for the parallel
-// parts; the sequential sums of BOTH tetrads run in warp 0 — lanes 0-15 tetrad A, lanes 16-31
-// tetrad B — so one instruction stream advances 2 x 11 chains.  18 tetrads resident per SM.
-__global__ void __launch_bounds__(kSupThreads, 9) superpose_kernel(SupArgs A) {
-    __shared__ double buf[2][6][kSupRow];   // rows 0-2: avg (then centred), rows 3-5: x (then centred)
-    __shared__ double zero_row[kSupRow];
-    __shared__ double sC[2][6];
-    __shared__ double sR[2][9];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int g = tid >> 6, gt = tid & 63;             // tetrad slot of this thread, thread index inside it
+// Per parameter set, once at upload: centroid of the average structure and G_ref = sum |avg_c|^2
+// (CenterCoords + the G1 sum of InnerProduct, qcprot.c:370-386,132-157) — the same for every tetrad
+// that shares the set, so superpose_kernel does not repeat these four 252-step chains.
+__global__ void ps_precompute_kernel(ParamSets ps, int P, double* pre) {
+    const int lane = threadIdx.x & 31;
+    const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const int S = ps.S, na = ps.na[p];
+    const double* AV = ps.avg + (size_t)p * 3 * S;
+    const double s = seq_sum1(AV + (size_t)(lane < 3 ? lane : 0) * S, na);
+    const double c = s / na;
+    const double c0 = __shfl_sync(0xffffffffu, c, 0), c1 = __shfl_sync(0xffffffffu, c, 1), c2 = __shfl_sync(0xffffffffu, c, 2);
+    double g = 0.0;
+    for (int i = 0; i < na; i++) {
+        const double a0 = AV[i] - c0, a1 = AV[S + i] - c1, a2 = AV[2 * S + i] - c2;
+        g = g + ((a0 * a0 + a1 * a1) + a2 * a2);
+    }
+    if (lane < 3) pre[4 * (size_t)p + lane] = c;
+    if (lane == 3) pre[4 * (size_t)p + 3] = g;
+}
+cudaError_t launch_ps_precompute(const ParamSets& ps, int P, double* pre, cudaStream_t st) {
+    if (P <= 0) return cudaSuccess;
+    ps_precompute_kernel<<<(P + 3) / 4, 128, 0, st>>>(ps, P, pre);
+    return cudaGetLastError();
+}
+
+// One warp per tetrad.  The sequential sums of the reference (centroid, 3x3 covariance + norm,
+// offset vector) are 252-step dependent DADD chains; each of them runs in ONE lane, the chains of a
+// phase side by side in lanes 0..9, and many warps per SM hide the 8-cycle add latency.  The
+// per-atom terms that feed a chain are produced 32 atoms at a time by all 32 lanes and handed over
+// through a [10][33] shared tile, so a chain step is one LDS + one DADD.
+struct SupSmem {
+    double x[3][kSupRow];          // coordinates, centred in place
+    double tile[10][kTileRow];
+};
+
+__global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A) {
+    __shared__ SupSmem sm_all[kSupWarps];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * kSupWarps + warp;
+    if (e >= A.count) return;
+    SupSmem& sm = sm_all[warp];
+    const unsigned full = 0xffffffffu;
     const int S = A.ps.S;
-    const int e = 2 * blockIdx.x + g;
-    const bool have = e < A.count;
-    const int t = A.t0 + (have ? e : 2 * blockIdx.x);  // slot B of an odd tail repeats tetrad A (results unused)
+    const int t = A.t0 + e;
     const int ps = A.param_id[t];
     const int na = A.ps.na[ps];
     const double* X = A.crd + (size_t)t * 3 * S;
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
-    constexpr int R4 = kMaxStride / 64;
+    const double* PRE = A.ps.pre + 4 * (size_t)ps;
+    const double ca0 = PRE[0], ca1 = PRE[1], ca2 = PRE[2], g_ref = PRE[3];
 
-    for (int i = tid; i < kSupRow; i += kSupThreads) zero_row[i] = 0.0;
 #pragma unroll
-    for (int r = 0; r < R4; r++) {
-        const int i = gt + 64 * r;
-        if (i < na) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { buf[g][c][i] = AV[c * S + i]; buf[g][3 + c][i] = X[c * S + i]; }
-        }
+    for (int r = 0; r < kMaxStride / 32; r++) {
+        const int i = lane + 32 * r;
+        if (i < na) { sm.x[0][i] = X[i]; sm.x[1][i] = X[S + i]; sm.x[2][i] = X[2 * S + i]; }
     }
-    __syncthreads();
-    // chain lanes: half h = lane / 16 works on tetrad slot h with its own atom count
-    const int h = lane >> 4, k = lane & 15;
-    int na_h = na;
-    if (tid < 32) {
-        const int eh = 2 * blockIdx.x + h;
-        const int th = A.t0 + (eh < A.count ? eh : 2 * blockIdx.x);
-        na_h = A.ps.na[A.param_id[th]];
-        // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
-        const double s = seq_sum1(buf[h][k < 6 ? k : 0], na_h);
-        if (k < 6) sC[h][k] = s / na_h;
+    __syncwarp();
+    double cx0, cx1, cx2;
+    {   // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
+        const double s = seq_sum1(sm.x[lane < 3 ? lane : 0], na);
+        const double c = s / na;
+        cx0 = __shfl_sync(full, c, 0); cx1 = __shfl_sync(full, c, 1); cx2 = __shfl_sync(full, c, 2);
     }
-    __syncthreads();
-    double ca[3], cx[3];
+    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 3; c++) { ca[c] = sC[g][c]; cx[c] = sC[g][3 + c]; }
-#pragma unroll
-    for (int r = 0; r < R4; r++) {   // centre in place (qcprot.c:382-386)
-        const int i = gt + 64 * r;
-        if (i < na) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) { buf[g][c][i] = buf[g][c][i] - ca[c]; buf[g][3 + c][i] = buf[g][3 + c][i] - cx[c]; }
-        }
+    for (int r = 0; r < kMaxStride / 32; r++) {   // centre in place (qcprot.c:382-386)
+        const int i = lane + 32 * r;
+        if (i < na) { sm.x[0][i] = sm.x[0][i] - cx0; sm.x[1][i] = sm.x[1][i] - cx1; sm.x[2][i] = sm.x[2][i] - cx2; }
     }
-    __syncthreads();
-    if (tid < 32) {   // InnerProduct, qcprot.c:132-157: lanes 0-8 the 3x3 products, 9 and 10 the two norms
-        const double* z = zero_row;
-        const double *p1, *q1, *p2 = z, *q2 = z, *p3 = z, *q3 = z;
-        if (k < 9) { p1 = buf[h][k / 3]; q1 = buf[h][3 + k % 3]; }
-        else if (k == 9) { p1 = q1 = buf[h][0]; p2 = q2 = buf[h][1]; p3 = q3 = buf[h][2]; }
-        else if (k == 10) { p1 = q1 = buf[h][3]; p2 = q2 = buf[h][4]; p3 = q3 = buf[h][5]; }
-        else { p1 = q1 = z; }
-        const double s = seq_sum3(p1, q1, p2, q2, p3, q3, na_h);
-        double m[11];
-#pragma unroll
-        for (int j = 0; j < 11; j++) m[j] = __shfl_sync(0xffffffffu, s, (lane & 16) + j);
-        double R[9];
-        qcp_rotation(R, m, (m[9] + m[10]) * 0.5);
-        if (k == 0) {
-#pragma unroll
-            for (int j = 0; j < 9; j++) sR[h][j] = R[j];
-        }
-    }
-    __syncthreads();
+    __syncwarp();
+
     double R[9];
+    {   // InnerProduct, qcprot.c:132-157: chains 0-8 the 3x3 products avg_c (x) x_c, chain 9 the norm of x_c
+        double acc = 0.0;
+        for (int b = 0; b < na; b += 32) {
+            const int i = b + lane;
+            double v[10];
 #pragma unroll
-    for (int j = 0; j < 9; j++) R[j] = sR[g][j];
+            for (int k = 0; k < 10; k++) v[k] = 0.0;
+            if (i < na) {
+                const double a0 = AV[i] - ca0, a1 = AV[S + i] - ca1, a2 = AV[2 * S + i] - ca2;
+                const double x0 = sm.x[0][i], x1 = sm.x[1][i], x2 = sm.x[2][i];
+                v[0] = a0 * x0; v[1] = a0 * x1; v[2] = a0 * x2;
+                v[3] = a1 * x0; v[4] = a1 * x1; v[5] = a1 * x2;
+                v[6] = a2 * x0; v[7] = a2 * x1; v[8] = a2 * x2;
+                v[9] = (x0 * x0 + x1 * x1) + x2 * x2;
+            }
 #pragma unroll
-    for (int r = 0; r < R4; r++) {   // offset-vector terms on the UNCENTRED arrays (re-read, L2-resident), edmd.cpp:97-101
-        const int i = gt + 64 * r;
+            for (int k = 0; k < 10; k++) sm.tile[k][lane] = v[k];
+            __syncwarp();
+            const int cnt = na - b < 32 ? na - b : 32;
+            if (lane < 10) acc = tile_chain(acc, sm.tile[lane], cnt);
+            __syncwarp();
+        }
+        double m[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) m[j] = __shfl_sync(full, acc, j);
+        const double g_x = __shfl_sync(full, acc, 9);
+        qcp_rotation(R, m, (g_ref + g_x) * 0.5);
+    }
+
+    double off = 0.0;   // offset-vector terms on the UNCENTRED arrays (re-read, L2-resident), edmd.cpp:97-101
+    for (int b = 0; b < na; b += 32) {
+        const int i = b + lane;
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
         if (i < na) {
             const double a0 = AV[i], a1 = AV[S + i], a2 = AV[2 * S + i];
             const double x0 = X[i], x1 = X[S + i], x2 = X[2 * S + i];
-            buf[g][0][i] = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
-            buf[g][1][i] = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
-            buf[g][2][i] = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
+            w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
+            w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
+            w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
         }
+        sm.tile[0][lane] = w0; sm.tile[1][lane] = w1; sm.tile[2][lane] = w2;
+        __syncwarp();
+        const int cnt = na - b < 32 ? na - b : 32;
+        if (lane < 3) off = tile_chain(off, sm.tile[lane], cnt);
+        __syncwarp();
     }
-    __syncthreads();
-    if (tid < 32) {
-        const double s = seq_sum1(buf[h][k < 3 ? k : 0], na_h);
-        const int eh = 2 * blockIdx.x + h;
-        if (eh < A.count) {
-            double* out = A.sup + (size_t)(A.t0 + eh) * kSupWords;
-            if (k < 3) out[9 + k] = s / na_h;          // edmd.cpp:102
-            if (k < 9) out[k] = sR[h][k];
-            if (k < 6) out[12 + k] = sC[h][k];
-        }
+
+    double* out = A.sup + (size_t)t * kSupWords;
+#pragma unroll
+    for (int j = 0; j < 9; j++) if (lane == j) out[j] = R[j];
+    if (lane < 3) {
+        out[9 + lane] = off / na;                                            // edmd.cpp:102
+        out[12 + lane] = lane == 0 ? ca0 : lane == 1 ? ca1 : ca2;
+        out[15 + lane] = lane == 0 ? cx0 : lane == 1 ? cx1 : cx2;
     }
 }
 
@@ -606,7 +641,7 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
                              cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
-    superpose_kernel<<<(count + 1) / 2, kSupThreads, 0, st>>>(B);
+    superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
     static const bool force_cta = getenv("EDMD_ED_CTA") != nullptr;   // A/B switch for tools/probe_perf.py

@@ -44,6 +44,11 @@ struct Timer {
     std::vector<cudaEvent_t> ev;   // start/stop pairs not yet folded
     double total_ms = 0.0;
     long long launches = 0;
+    long long graph_launches = 0;   // kernel launches inside one replay of the step graph
+    double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
+    double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
+    cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
+    cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
 };
 
 template <class T>
@@ -79,7 +84,7 @@ struct edmd_engine {
     bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     unsigned char *d_mark = nullptr, *d_dirty = nullptr;
-    double* d_gb = nullptr;                 // [n][8][4] group bounding spheres (scan mode 4)
+    double* d_gb = nullptr;                 // [n][8][4] group + [n][4] tetrad bounding spheres (scan mode 4)
     int* d_perm = nullptr;                  // [P][S] slot -> atom, compact groups of 32 (scan mode 4)
     unsigned long long* d_pmask = nullptr;  // [pairs_cap] 8x8 group masks per pair (scan mode 4)
     long long pmask_cap = 0;   // per-tetrad: in a flagged pair now / fnb non-zero
@@ -128,7 +133,7 @@ struct edmd_engine {
     int rank = 1;
     long calls = 0;
 
-    int scan_mode = 1;   // 0 direct, 1 gram (see nb.cu)
+    int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
     bool use_graph = true, graph_valid = false;
     int graph_random_mode = -1;
@@ -140,6 +145,11 @@ struct edmd_engine {
     bool timing = false;
     Timer timers[T_COUNT];
     long long launches = 0;
+    long long graph_launches = 0;   // kernel launches inside one replay of the step graph
+    double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
+    double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
+    cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
+    cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
 };
 
 namespace {
@@ -181,6 +191,8 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
     cudaFree(e->d_perm); e->d_perm = nullptr;
     cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
+    cudaFree(e->d_noise); e->d_noise = nullptr; e->noise_valid = false;
+    cudaFree(e->d_pspre); e->d_pspre = nullptr;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -374,6 +386,15 @@ int do_finish(edmd_engine* e) {
     e->latest_in_crd2 = true;
     return 0;
 }
+// per-parameter-set table of Langevin noise amplitudes (rng.cu); depends on gamma, kT and dt
+int ensure_noise(edmd_engine* e) {
+    if (e->noise_valid) return 0;
+    if (!e->d_noise) CK(dev_alloc(&e->d_noise, (size_t)e->P * 3 * e->S));
+    CK(launch_noise_table(e->ps, e->P, e->d_noise, e->sp, e->st));
+    e->launches++;
+    e->noise_valid = true;
+    return 0;
+}
 int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before, const long* calls_dev = nullptr) {
     if (mode == 0) {
         if (!e->rnd_zero) {
@@ -383,8 +404,9 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before,
         return 0;
     }
     if (mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown (0 = off, 1 = reference stream)", mode);
+    if (int rc = ensure_noise(e)) return rc;
     timer_begin(e, T_RNG);
-    CK(launch_random_terms(e->ps, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
+    CK(launch_random_terms(e->ps, e->d_noise, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
                            calls_before + e->t0, calls_dev, e->st));
     timer_end(e, T_RNG, 1);
     e->rnd_zero = false;
@@ -455,6 +477,8 @@ void edmd_destroy(edmd_engine* e) {
     free_system(e);
     if (e->span0) { cudaEventDestroy(e->span0); cudaEventDestroy(e->span1); }
     for (cudaEvent_t ev : e->marks) cudaEventDestroy(ev);
+    if (e->st_copy) cudaStreamDestroy(e->st_copy);
+    if (e->ev_crd_in) { cudaEventDestroy(e->ev_crd_in); cudaEventDestroy(e->ev_vel_in); }
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -465,6 +489,7 @@ int edmd_set_params(edmd_engine* e, const edmd_params* p) {
     e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
     e->sp.mole_least = p->mole_Least;
     e->hits_valid = false;
+    e->noise_valid = false;
     drop_graph(e);
     return 0;
 }
@@ -609,7 +634,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
     CK(dev_alloc(&e->d_mark, (size_t)n)); CK(dev_alloc(&e->d_dirty, (size_t)n));
-    CK(dev_alloc(&e->d_gb, (size_t)n * 32));
+    CK(dev_alloc(&e->d_gb, (size_t)n * 36));
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)n, e->st));   // unknown force contents: treat as dirty
     CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
     CK(dev_alloc(&e->d_stage, 3 * (size_t)e->total3));
@@ -635,6 +660,9 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     e->rnd_zero = true;
 
     e->ps = ParamSets{e->d_ps_na, e->d_ps_nev, e->d_avg, e->d_mass, e->d_chg, e->d_eval, e->d_evec, S, NEV};
+    CK(dev_alloc(&e->d_pspre, (size_t)P * 4));
+    e->ps.pre = e->d_pspre;
+    CK(launch_ps_precompute(e->ps, P, e->d_pspre, e->st));
     e->t0 = 0; e->t1 = n; e->p0 = e->p1 = 0; e->shard_pairs_custom = false;
     if (int rc = upload_order(e)) return rc;
 
@@ -1028,7 +1056,7 @@ int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
 static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     if (int rc = do_ed(e)) return rc;
     if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
-    if (random_mode == 1 && calls_dev) CK(launch_bump_counter(e->d_calls, (long)e->n, e->st));
+    if (random_mode == 1 && calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
     if (int rc = do_scan(e)) return rc;
     return do_finish(e);
 }
@@ -1044,7 +1072,7 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (int rc = check_ready(e, true)) return rc;
     if (random_mode != 0 && random_mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown", random_mode);
     CK(cudaSetDevice(e->device));
-    const bool graph_ok = e->use_graph && !e->timing && e->nb_clip && nsteps > 1;
+    const bool graph_ok = e->use_graph && !e->timing && e->nb_clip && !e->peer_mode && nsteps >= 1;
     if (!graph_ok) {
         for (int it = 0; it < nsteps; it++) {
             if (int rc = one_step(e, random_mode, nullptr)) return rc;
@@ -1064,11 +1092,15 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (random_mode == 0) { if (int rc = do_random(e, 0, 0, 0, 0)) return rc; }
     if (!e->d_calls) CK(dev_alloc(&e->d_calls, 1));
     CK(cudaMemcpyAsync(e->d_calls, &e->calls, sizeof(long), cudaMemcpyHostToDevice, e->st));
+    if (random_mode == 1) if (int rc = ensure_noise(e)) return rc;   // not inside the capture
     if (!e->graph_valid || e->graph_random_mode != random_mode) {
         drop_graph(e);
         CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
         const bool zero_flag = e->rnd_zero;
+        const long long counted = e->launches;
         int rc = one_step(e, random_mode, e->d_calls);
+        e->graph_launches = e->launches - counted;   // kernels in one captured step (nothing ran yet)
+        e->launches = counted;
         cudaError_t end = cudaStreamEndCapture(e->st, &e->graph);
         e->rnd_zero = random_mode == 0 ? zero_flag : false;
         if (rc) { if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; } return rc; }
@@ -1078,11 +1110,56 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
         e->latest_in_crd2 = true;
     }
     for (int it = 0; it < nsteps; it++) CK(cudaGraphLaunch(e->graph_exec, e->st));
-    e->launches += (long long)nsteps * (random_mode == 1 ? 8 : 6);
+    e->launches += (long long)nsteps * e->graph_launches;
     if (random_mode == 1) { e->calls += (long)nsteps * e->n; e->rnd_zero = false; }
     e->latest_in_crd2 = true;
     e->hits_valid = false;
     return 0;
+}
+
+// One call = upload the caller's state, run the steps, read the state back (what Master does around
+// calculate_Forces with its host Tetrad array, master.cpp:268-343).  Because the host buffers are
+// only touched inside the call, the transfers are pipelined with the kernels: coordinates go up
+// first, the velocities follow on a second stream while the ED and distance kernels (which do not
+// read them) run, and the finish kernel waits for them.
+int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int random_mode) {
+    if (int rc = check_ready(e, true)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_step_host: n=%d but engine holds %d tetrads", n, e->n);
+    if (nsteps < 1) return fail(EDMD_ERR_ARG, "edmd_step_host: nsteps must be >= 1");
+    if (random_mode != 0 && random_mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown", random_mode);
+    const bool pipelined = dense_field(e, tets, 0) && dense_field(e, tets, 1) && e->nb_clip && !e->peer_mode && !e->timing;
+    if (!pipelined) {
+        if (int rc = edmd_set_state(e, tets, n)) return rc;
+        if (int rc = edmd_step(e, nsteps, random_mode)) return rc;
+        return edmd_get_state(e, tets, n);
+    }
+    CK(cudaSetDevice(e->device));
+    if (!e->st_copy) {
+        CK(cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_crd_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_vel_in, cudaEventDisableTiming));
+    }
+    e->latest_in_crd2 = false;                       // the device state is replaced as a whole
+    const size_t bytes = sizeof(double) * e->total3;
+    CK(cudaMemcpyAsync(e->d_stage, tets[0].coordinates, bytes, cudaMemcpyHostToDevice, e->st));
+    CK(cudaEventRecord(e->ev_crd_in, e->st));
+    CK(launch_pack_planes(e->d_stage, e->d_off3, e->d_natoms, e->crd, e->n, e->S, e->st));
+    CK(cudaStreamWaitEvent(e->st_copy, e->ev_crd_in, 0));          // one upload at a time on the link
+    CK(cudaMemcpyAsync(e->d_stage + e->total3, tets[0].velocities, bytes, cudaMemcpyHostToDevice, e->st_copy));
+    CK(launch_pack_planes(e->d_stage + e->total3, e->d_off3, e->d_natoms, e->vel, e->n, e->S, e->st_copy));
+    CK(cudaEventRecord(e->ev_vel_in, e->st_copy));
+    e->launches += 2;
+    e->hits_valid = false;
+    // first step as separate launches so that the finish kernel alone waits for the velocities
+    if (int rc = do_ed(e)) return rc;
+    if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, nullptr)) return rc;
+    if (int rc = do_scan(e)) return rc;
+    CK(cudaStreamWaitEvent(e->st, e->ev_vel_in, 0));
+    if (int rc = do_finish(e)) return rc;
+    if (random_mode == 1) e->calls += e->n;
+    e->hits_valid = false;
+    if (nsteps > 1) if (int rc = edmd_step(e, nsteps - 1, random_mode)) return rc;
+    return edmd_get_state(e, tets, n);
 }
 
 int edmd_sync(edmd_engine* e) {

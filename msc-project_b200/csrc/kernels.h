@@ -68,9 +68,11 @@ cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const 
                                long long np, int2* pairs, void** tmp, size_t* tmp_bytes, cudaStream_t st);
 
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
-cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
+cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
                                 const long* calls_dev, cudaStream_t st);
+cudaError_t launch_ps_precompute(const ParamSets& ps, int P, double* pre, cudaStream_t st);
+cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const SimParams& sp, cudaStream_t st);
 cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st);
 
 // interleaved xyz (reference layout, tetrads concatenated at off3[t]) <-> SoA planes

@@ -261,8 +261,10 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 // inside a pair, every (register group, partner group) block whose spheres are too far apart.
 // Conservative by construction (spheres contain their atoms, the test is inflated by 1e-9), so the
 // selected pairs remain a superset of the true hits and the final forces are bit-identical.
-// Work is no longer the reference's 63,504 atom pairs per listed pair — this mode is opt-in
-// (edmd_set_nb_scan_mode(4)) and reported separately from the brute-force headline.
+// A pair of whole-tetrad spheres is tested first, so the typical far-apart listed pair costs one
+// sphere test.  Results are bit-identical to the brute-force modes (tests/test_gpu_edge.py), so
+// this is the engine's default; modes 0-2 evaluate all 63,504 atom pairs of every listed pair
+// and are kept for the roofline measurement of the distance kernel (bench.py `variants`).
 __global__ void group_bounds_kernel(const double* crd, const int* natoms, const int* param_id, const int* perm,
                                     double* gb, int n, int S) {
     const int lane = threadIdx.x & 31;
@@ -270,6 +272,8 @@ __global__ void group_bounds_kernel(const double* crd, const int* natoms, const 
     if (t >= n) return;
     const double* X = crd + (size_t)t * 3 * S;
     const int* PM = perm + (size_t)param_id[t] * S;
+    double tx = 0.0, ty = 0.0, tz = 0.0; int tn = 0;          // lane g keeps group g's sphere for the tetrad sphere
+    double gx = 0.0, gy = 0.0, gz = 0.0, gr = -1.0;
     for (int g = 0; g < 8; g++) {
         const int a = PM[32 * g + lane];      // slot -> atom (spatially compact groups), -1 = empty slot
         const bool on = a >= 0;
@@ -292,15 +296,37 @@ __global__ void group_bounds_kernel(const double* crd, const int* natoms, const 
             double* out = gb + ((size_t)t * 8 + g) * 4;
             out[0] = cx; out[1] = cy; out[2] = cz; out[3] = rad;
         }
+        if (cnt > 0) { tx += cx; ty += cy; tz += cz; tn++; }
+        if (lane == g) { gx = cx; gy = cy; gz = cz; gr = rad; }
+    }
+    // tetrad sphere: centre = mean of the group centres, radius = max over groups of (distance + group radius)
+    double trad = -1.0;
+    if (tn > 0) {
+        tx /= tn; ty /= tn; tz /= tn;
+        double reach = gr >= 0.0 ? sqrt((gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz)) + gr : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) reach = fmax(reach, __shfl_xor_sync(0xffffffffu, reach, o));
+        trad = reach * (1.0 + 1e-12) + 1e-12;
+    }
+    if (lane == 0) {
+        double* out = gb + (size_t)n * 32 + (size_t)t * 4;
+        out[0] = tx; out[1] = ty; out[2] = tz; out[3] = trad;
     }
 }
 
 __global__ void pair_masks_kernel(const double* gb, const int2* pairs, long long p0, long long p1, double dcut,
-                                  unsigned long long* mask) {
+                                  unsigned long long* mask, int n) {
     const long long k = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p1) return;
     const int2 pr = pairs[k];
     const int tr = pr.x < pr.y ? pr.x : pr.y, ts = pr.x < pr.y ? pr.y : pr.x;
+    {   // whole-tetrad spheres first: one test instead of 64 for the (typical) far-apart pair
+        const double4* TB = reinterpret_cast<const double4*>(gb) + (size_t)n * 8;
+        const double4 a = TB[tr], b = TB[ts];
+        const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+        const double lim = a.w + b.w + dcut;
+        if (a.w < 0.0 || b.w < 0.0 || dx * dx + dy * dy + dz * dz > lim * lim * (1.0 + 1e-9)) { mask[k] = 0ull; return; }
+    }
     const double4* R = reinterpret_cast<const double4*>(gb) + (size_t)tr * 8;
     const double4* P = reinterpret_cast<const double4*>(gb) + (size_t)ts * 8;
     double4 rr[8];
@@ -439,7 +465,7 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     }
     group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S);
     const long long want = p1 - p0;
-    pair_masks_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), mask);
+    pair_masks_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), mask, n);
     long long chunk = want / ((long long)sms * 64);
     if (chunk < 1) chunk = 1;
     if (chunk > 16) chunk = 16;

@@ -32,8 +32,20 @@ __device__ __forceinline__ unsigned lfg_next_block(unsigned P, int lane) {
     return s + tail;   // lane 31 carries garbage and is never read
 }
 
+// x / RAND_MAX (edmd.cpp:206-207) for an integer 0 <= x < 2^31 without the division sequence:
+// q0 = x * RN(1/M), one exact-residual correction.  The result equals the correctly rounded
+// quotient x / 2147483647.0 for EVERY such x (exhaustive check: tests/cpp/div_rand_max.c, run by
+// tests/test_oracle.py) — 3 FP64 instructions instead of ~25.
+__device__ __forceinline__ double div_rand_max(double x) {
+    const double M = 2147483647.0, c = 1.0 / 2147483647.0;
+    const double q0 = __dmul_rn(x, c);
+    const double r = __fma_rn(-q0, M, x);
+    return __fma_rn(r, c, q0);
+}
+
 struct RngArgs {
     ParamSets ps;
+    const double* noise; // [P][3][S] sqrt(2*gamma*kT*m/dt), launch_noise_table
     const int* param_id;
     double* rnd;         // [n][3][S]
     int t0, count;
@@ -52,7 +64,7 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
     const int ps = A.param_id[t];
     const int S = A.ps.S;
     const int n3 = 3 * A.ps.na[ps];
-    const double* M = A.ps.mass + (size_t)ps * 3 * S;
+    const double* NZ = A.noise + (size_t)ps * 3 * S;
     double* out = A.rnd + (size_t)t * 3 * S;
 
     // seed: RNG_Seed starts at 13579, ++ per call, reset to 13579 once it exceeds 50,000,000
@@ -91,8 +103,8 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
         bool accept = false;
         double z = 0.0;
         if (lane < 31) {   // edmd.cpp:206-216
-            const double u = (double)(int)o0 / 2147483647.0;
-            double v = (double)(int)o1 / 2147483647.0;
+            const double u = div_rand_max((double)(int)o0);
+            double v = div_rand_max((double)(int)o1);
             v = __dmul_rn(1.7156, __dsub_rn(v, 0.5));
             const double x = __dsub_rn(u, 0.449871);
             const double y = __dadd_rn(fabs(v), 0.386595);
@@ -108,20 +120,31 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
             const int idx = k + __popc(acc & ((1u << lane) - 1u));
             if (idx < n3) {
                 const int a = idx / 3, cc = idx - 3 * a;
-                const double m = M[cc * S + a];
-                const double noise = sqrt(2.0 * A.gamma * A.scaled * m / A.dt);   // edmd.cpp:184
-                out[cc * S + a] = __dmul_rn(z, noise);                            // :223
+                out[cc * S + a] = __dmul_rn(z, NZ[cc * S + a]);                   // edmd.cpp:223
             }
         }
         k += __popc(acc);
     }
 }
 
-cudaError_t launch_random_terms(const ParamSets& ps, const int* param_id, double* rnd, int t0, int count,
+// noise[p][c][a] = sqrt(2*gamma*kT*m/dt), edmd.cpp:184 — one table per parameter set instead of one
+// square root per deviate (IEEE operations in the reference's order, so the same bits).
+__global__ void noise_table_kernel(const double* mass, double* noise, long total, double gamma, double scaled, double dt) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) noise[i] = sqrt(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, gamma), scaled), mass[i]), dt));
+}
+cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const SimParams& sp, cudaStream_t st) {
+    const long total = (long)P * 3 * ps.S;
+    if (total <= 0) return cudaSuccess;
+    noise_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ps.mass, noise, total, sp.gamma, sp.scaled, sp.dt);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
                                 const long* calls_dev, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    RngArgs A{ps, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before, calls_dev};
+    RngArgs A{ps, noise, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before, calls_dev};
     const int wpb = 4;
     random_terms_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, st>>>(A);
     return cudaGetLastError();

@@ -72,6 +72,7 @@ def load_library():
         "edmd_set_nb_consts": (C.c_int, [E, C.c_double, C.c_double]),
         "edmd_set_nb_clip": (C.c_int, [E, C.c_int]),
         "edmd_set_nb_scan_mode": (C.c_int, [E, C.c_int]),
+        "edmd_step_host": (C.c_int, [E, C.c_void_p, C.c_int, C.c_int, C.c_int]),
         "edmd_upload_tetrads": (C.c_int, [E, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
         "edmd_set_state": (C.c_int, [E, C.c_void_p, C.c_int]),
         "edmd_get_state": (C.c_int, [E, C.c_void_p, C.c_int]),
@@ -388,6 +389,11 @@ class Engine:
 
     def step(self, nsteps=1, random_mode=0):
         self._ck(self.lib.edmd_step(self.h, nsteps, random_mode))
+
+    def step_host(self, nsteps=1, random_mode=0):
+        """edmd_step_host: the host Tetrad block (self.block.crd / .vel) in, stepped, and back in place."""
+        self._ck(self.lib.edmd_step_host(self.h, self.block.ptr, self.sys.n, nsteps, random_mode))
+        return self.block.crd, self.block.vel
 
     def set_graph(self, on: bool):
         self._ck(self.lib.edmd_set_graph(self.h, int(on)))

@@ -191,3 +191,18 @@ def test_cell_list_builder_large_ring(edmd):
     sep = np.abs(p[:, 0] - p[:, 1]); sep = np.minimum(sep, s.n - sep)
     assert sep.min() == 6
     assert np.all(np.diff(np.minimum(p[:, 0], p[:, 1])) >= 0)     # rows ascending
+
+
+def test_step_host_matches_the_three_separate_calls(edmd, ragged):
+    """edmd_step_host (pipelined uploads) == edmd_set_state + edmd_step + edmd_get_state, bit for bit,
+    starting from the same host Tetrad arrays, over several calls, with and without random forces."""
+    for random_mode in (0, 1):
+        a = edmd.Engine(ragged); a.build_pairlist(); a.set_rng(123, 1, 0)
+        b = edmd.Engine(ragged); b.build_pairlist(); b.set_rng(123, 1, 0)
+        for nsteps in (1, 3, 1):
+            a.step_host(nsteps, random_mode)                       # host block in -> stepped -> host block
+            b.push_state(); b.step(nsteps, random_mode); b.get_state(copy=False)
+            assert np.array_equal(a.block.crd, b.block.crd) and np.array_equal(a.block.vel, b.block.vel)
+        a.merge(); b.merge()                                        # the device state is consistent afterwards
+        (ca, va), (cb, vb) = a.get_state(), b.get_state()
+        assert np.array_equal(ca, cb) and np.array_equal(va, vb)

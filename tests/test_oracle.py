@@ -166,3 +166,18 @@ def test_multithreaded_baseline_matches_serial(edmd, po):
     a = po.Oracle(s, "port"); a.build_pairs(); a.step(2, nthreads=1)
     b = po.Oracle(s, "port"); b.build_pairs(); b.step(2, nthreads=4)
     assert np.allclose(a.get_state()[0], b.get_state()[0], rtol=1e-12, atol=1e-12)
+
+
+def test_division_free_rand_max_quotient_is_exact(tmp_path):
+    """rng.cu replaces rand()/RAND_MAX's division by an FMA-corrected product; it must give the
+    correctly rounded quotient for every possible rand() value (all 2^31 of them, ~2 s threaded)."""
+    import os, subprocess
+    if " fma " not in open("/proc/cpuinfo").read():
+        pytest.skip("host CPU has no FMA unit: the exhaustive loop would run on libm's software fma")
+    src = os.path.join(os.path.dirname(__file__), "cpp", "div_rand_max.c")
+    exe = str(tmp_path / "div_rand_max")
+    # -ffp-contract=off: the products and sums in the checker must round like the CUDA intrinsics
+    subprocess.run(["/usr/bin/gcc", "-O2", "-fopenmp", "-mfma", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == 0          # corrected form: no mismatch
+    assert int(out[1]) > 0           # (the plain product alone is NOT exact - the correction matters)
