@@ -221,6 +221,10 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
         if (i < na) { sm.x[0][i] = X[i]; sm.x[1][i] = X[S + i]; sm.x[2][i] = X[2 * S + i]; }
     }
     __syncwarp();
+    // global operands of the next 32-atom block are fetched one block ahead of their use, so their
+    // L2 latency hides behind the running chains
+    double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0;
+    if (lane < na) { pa0 = AV[lane]; pa1 = AV[S + lane]; pa2 = AV[2 * S + lane]; }
     double cx0, cx1, cx2;
     {   // CenterCoords, qcprot.c:370-379: sum in atom order, then divide by len
         const double s = seq_sum1(sm.x[lane < 3 ? lane : 0], na);
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
     __syncwarp();
 
     double R[9];
+    double px0 = 0.0, px1 = 0.0, px2 = 0.0;
     {   // InnerProduct, qcprot.c:132-157: chains 0-8 the 3x3 products avg_c (x) x_c, chain 9 the norm of x_c
         double acc = 0.0;
         for (int b = 0; b < na; b += 32) {
@@ -243,8 +248,10 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
             double v[10];
 #pragma unroll
             for (int k = 0; k < 10; k++) v[k] = 0.0;
+            const double r0 = pa0, r1 = pa1, r2 = pa2;
+            if (i + 32 < na) { pa0 = AV[i + 32]; pa1 = AV[S + i + 32]; pa2 = AV[2 * S + i + 32]; }
             if (i < na) {
-                const double a0 = AV[i] - ca0, a1 = AV[S + i] - ca1, a2 = AV[2 * S + i] - ca2;
+                const double a0 = r0 - ca0, a1 = r1 - ca1, a2 = r2 - ca2;
                 const double x0 = sm.x[0][i], x1 = sm.x[1][i], x2 = sm.x[2][i];
                 v[0] = a0 * x0; v[1] = a0 * x1; v[2] = a0 * x2;
                 v[3] = a1 * x0; v[4] = a1 * x1; v[5] = a1 * x2;
@@ -262,6 +269,10 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
 #pragma unroll
         for (int j = 0; j < 9; j++) m[j] = __shfl_sync(full, acc, j);
         const double g_x = __shfl_sync(full, acc, 9);
+        if (lane < na) {   // first block of the offset pass, in flight during the quartic solve
+            pa0 = AV[lane]; pa1 = AV[S + lane]; pa2 = AV[2 * S + lane];
+            px0 = X[lane]; px1 = X[S + lane]; px2 = X[2 * S + lane];
+        }
         qcp_rotation(R, m, (g_ref + g_x) * 0.5);
     }
 
@@ -269,9 +280,12 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
     for (int b = 0; b < na; b += 32) {
         const int i = b + lane;
         double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+        const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
+        if (i + 32 < na) {
+            pa0 = AV[i + 32]; pa1 = AV[S + i + 32]; pa2 = AV[2 * S + i + 32];
+            px0 = X[i + 32]; px1 = X[S + i + 32]; px2 = X[2 * S + i + 32];
+        }
         if (i < na) {
-            const double a0 = AV[i], a1 = AV[S + i], a2 = AV[2 * S + i];
-            const double x0 = X[i], x1 = X[S + i], x2 = X[2 * S + i];
             w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
             w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
             w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
@@ -512,10 +526,11 @@ __device__ __forceinline__ constexpr int reduce12_owner(int j) {   // inverse of
     return 16 * (j / 6) + 8 * ((j % 6) / 3) + ((j % 3) == 2 ? 4 : 0) + ((j % 3) == 1 ? 2 : 0);
 }
 
+template <int SC>   // SC: the atom stride when it is the usual 256 (all shared-memory offsets fold into immediates), else 0
 __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) {
     extern __shared__ double wsm[];
     __shared__ int sNext;
-    const int S = A.ps.S;
+    const int S = SC ? SC : A.ps.S;
     double* sEV = wsm;               // [kNevReg][3][S]
     double* sAV = wsm + kNevReg * 3 * S;   // [3][S]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -649,15 +664,18 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
         const size_t smem = sizeof(double) * (kNevReg * 3 + 3) * ps.S;
         static bool configured = false;
         if (!configured) {
-            err = cudaFuncSetAttribute(ed_project_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(sizeof(double) * (kNevReg * 3 + 3) * kMaxStride));
+            const int most = (int)(sizeof(double) * (kNevReg * 3 + 3) * kMaxStride);
+            err = cudaFuncSetAttribute(ed_project_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+            if (err != cudaSuccess) return err;
+            err = cudaFuncSetAttribute(ed_project_warp_kernel<kMaxStride>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
             if (err != cudaSuccess) return err;
             configured = true;
         }
         int chunk = (count + 2 * sms - 1) / (2 * sms);   // two resident CTAs per SM, one wave
         if (chunk < kWarps) chunk = kWarps;              // at least one tetrad per warp
         EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
-        ed_project_warp_kernel<<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
+        if (ps.S == kMaxStride) ed_project_warp_kernel<kMaxStride><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
+        else                    ed_project_warp_kernel<0><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
         return cudaGetLastError();
     }
     int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer

@@ -86,7 +86,7 @@ struct edmd_engine {
     unsigned char *d_mark = nullptr, *d_dirty = nullptr;
     double* d_gb = nullptr;                 // [n][8][4] group + [n][4] tetrad bounding spheres (scan mode 4)
     int* d_perm = nullptr;                  // [P][S] slot -> atom, compact groups of 32 (scan mode 4)
-    unsigned long long* d_pmask = nullptr;  // [pairs_cap] 8x8 group masks per pair (scan mode 4)
+    unsigned long long* d_pmask = nullptr;  // counter + [pairs_cap] {pair index, 8x8 group mask} work items (scan mode 4)
     long long pmask_cap = 0;   // per-tetrad: in a flagged pair now / fnb non-zero
     bool rnd_zero = true;   // random terms currently all zero
 
@@ -243,7 +243,7 @@ int ensure_pair_capacity(edmd_engine* e, long long np) {
     e->d_pairs = nullptr; e->d_hit = nullptr; e->d_pmask = nullptr; e->pairs_cap = 0; e->pmask_cap = 0;
     CK(dev_alloc(&e->d_pairs, (size_t)cap));
     CK(dev_alloc(&e->d_hit, (size_t)cap));
-    CK(dev_alloc(&e->d_pmask, (size_t)cap));
+    CK(dev_alloc(&e->d_pmask, 2 * (size_t)cap + 2));   // counter slot + one {pair, mask} item per pair (nb.cu)
     e->pmask_cap = cap;
     e->pairs_cap = cap;
     return 0;
@@ -604,6 +604,19 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
         while (!jobs.empty()) {
             Job j = jobs.back(); jobs.pop_back();
             if (j.parts == 1) {
+                // slot 0 of the group = its 1-centre (smallest maximum distance to the other members):
+                // group_bounds_kernel centres the group's bounding sphere on that atom
+                int best = j.lo; double best_r = 1e300;
+                for (int q = j.lo; q < j.hi; q++) {
+                    double r2 = 0.0;
+                    for (int u = j.lo; u < j.hi; u++) {
+                        double d2 = 0.0;
+                        for (int c = 0; c < 3; c++) { const double d = T.avg[3 * idx[q] + c] - T.avg[3 * idx[u] + c]; d2 += d * d; }
+                        r2 = std::max(r2, d2);
+                    }
+                    if (r2 < best_r) { best_r = r2; best = q; }
+                }
+                if (j.hi > j.lo) std::swap(idx[j.lo], idx[best]);
                 for (int q = j.lo; q < j.hi && q - j.lo < 32; q++) perm[(size_t)p * S + 32 * j.first + (q - j.lo)] = idx[q];
                 continue;
             }

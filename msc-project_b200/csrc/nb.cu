@@ -265,89 +265,105 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 // sphere test.  Results are bit-identical to the brute-force modes (tests/test_gpu_edge.py), so
 // this is the engine's default; modes 0-2 evaluate all 63,504 atom pairs of every listed pair
 // and are kept for the roofline measurement of the distance kernel (bench.py `variants`).
-__global__ void group_bounds_kernel(const double* crd, const int* natoms, const int* param_id, const int* perm,
-                                    double* gb, int n, int S) {
+// One warp per tetrad.  Group g's sphere is centred on the atom in its slot 0 — the upload puts the
+// group's 1-centre there (the atom of the average structure with the smallest maximum distance to
+// the rest of its group), so no centroid reduction is needed — and its radius is the largest
+// distance to that atom, reduced in FP32 with every conversion rounded UP (a bound, not an estimate).
+__global__ void __launch_bounds__(128) group_bounds_kernel(const double* crd, const int* natoms, const int* param_id,
+                                                            const int* perm, double* gb, int n, int S) {
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
     const double* X = crd + (size_t)t * 3 * S;
     const int* PM = perm + (size_t)param_id[t] * S;
-    double tx = 0.0, ty = 0.0, tz = 0.0; int tn = 0;          // lane g keeps group g's sphere for the tetrad sphere
-    double gx = 0.0, gy = 0.0, gz = 0.0, gr = -1.0;
+    int a[8];
+#pragma unroll
+    for (int g = 0; g < 8; g++) a[g] = PM[32 * g + lane];     // slot -> atom, -1 = empty slot
+    double gx = 0.0, gy = 0.0, gz = 0.0, gr = -1.0;            // lane g keeps group g's sphere
+#pragma unroll
     for (int g = 0; g < 8; g++) {
-        const int a = PM[32 * g + lane];      // slot -> atom (spatially compact groups), -1 = empty slot
-        const bool on = a >= 0;
-        double x = on ? X[a] : 0.0, y = on ? X[S + a] : 0.0, z = on ? X[2 * S + a] : 0.0;
-        double sx = x, sy = y, sz = z; int cnt = on ? 1 : 0;
+        const bool on = a[g] >= 0;
+        const double x = on ? X[a[g]] : 0.0, y = on ? X[S + a[g]] : 0.0, z = on ? X[2 * S + a[g]] : 0.0;
+        const double cx = __shfl_sync(full, x, 0), cy = __shfl_sync(full, y, 0), cz = __shfl_sync(full, z, 0);
+        const bool any = __shfl_sync(full, (int)on, 0) != 0;   // slots fill from 0: empty slot 0 = empty group
+        const double d2 = on ? (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) : 0.0;
+        float f = __double2float_ru(d2);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o);
-            sz += __shfl_xor_sync(0xffffffffu, sz, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        }
-        double rad = -1.0, cx = 0.0, cy = 0.0, cz = 0.0;
-        if (cnt > 0) {
-            cx = sx / cnt; cy = sy / cnt; cz = sz / cnt;
-            double d2 = on ? (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) : 0.0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-            rad = sqrt(d2) * (1.0 + 1e-12) + 1e-12;
-        }
-        if (lane == 0) {
-            double* out = gb + ((size_t)t * 8 + g) * 4;
-            out[0] = cx; out[1] = cy; out[2] = cz; out[3] = rad;
-        }
-        if (cnt > 0) { tx += cx; ty += cy; tz += cz; tn++; }
+        for (int o = 16; o > 0; o >>= 1) f = fmaxf(f, __shfl_xor_sync(full, f, o));
+        const double rad = any ? (double)__fsqrt_ru(f) * (1.0 + 1e-12) + 1e-12 : -1.0;
+        if (lane == 0) *reinterpret_cast<double4*>(gb + ((size_t)t * 8 + g) * 4) = make_double4(cx, cy, cz, rad);
         if (lane == g) { gx = cx; gy = cy; gz = cz; gr = rad; }
     }
-    // tetrad sphere: centre = mean of the group centres, radius = max over groups of (distance + group radius)
+    // tetrad sphere: centre = mean of the non-empty group centres, radius = max over groups of
+    // (distance to the centre + group radius); lanes 0..7 hold the groups
+    const bool have = lane < 8 && gr >= 0.0;
+    double tx = have ? gx : 0.0, ty = have ? gy : 0.0, tz = have ? gz : 0.0; int tn = have ? 1 : 0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        tx += __shfl_xor_sync(full, tx, o); ty += __shfl_xor_sync(full, ty, o);
+        tz += __shfl_xor_sync(full, tz, o); tn += __shfl_xor_sync(full, tn, o);
+    }
     double trad = -1.0;
     if (tn > 0) {
-        tx /= tn; ty /= tn; tz /= tn;
-        double reach = gr >= 0.0 ? sqrt((gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz)) + gr : 0.0;
+        const double inv = (double)__frcp_rn((float)tn);       // any centre will do: the radius is measured from it
+        tx *= inv; ty *= inv; tz *= inv;
+        const double dd = (gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz);
+        float reach = have ? __fadd_ru(__fsqrt_ru(__double2float_ru(dd)), __double2float_ru(gr)) : 0.0f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) reach = fmax(reach, __shfl_xor_sync(0xffffffffu, reach, o));
-        trad = reach * (1.0 + 1e-12) + 1e-12;
+        for (int o = 4; o > 0; o >>= 1) reach = fmaxf(reach, __shfl_xor_sync(full, reach, o));
+        trad = (double)reach * (1.0 + 1e-12) + 1e-12;
     }
-    if (lane == 0) {
-        double* out = gb + (size_t)n * 32 + (size_t)t * 4;
-        out[0] = tx; out[1] = ty; out[2] = tz; out[3] = trad;
-    }
+    if (lane == 0) *reinterpret_cast<double4*>(gb + (size_t)n * 32 + (size_t)t * 4) = make_double4(tx, ty, tz, trad);
 }
 
-__global__ void pair_masks_kernel(const double* gb, const int2* pairs, long long p0, long long p1, double dcut,
-                                  unsigned long long* mask, int n) {
+// One thread per listed pair: whole-tetrad spheres first (one test instead of 64 for the typical
+// far-apart pair), then the 8 x 8 group spheres.  Pairs with a non-empty mask are appended to a
+// compact work list {pair index, mask} (warp-aggregated atomic; the order of the list varies from
+// run to run, the set — and therefore every hit flag — does not).
+struct CullItem { long long k; unsigned long long mask; };
+
+__global__ void __launch_bounds__(128) pair_select_kernel(const double* gb, const int2* pairs, long long p0, long long p1,
+                                                          double dcut, CullItem* items, unsigned* count, int n) {
     const long long k = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= p1) return;
-    const int2 pr = pairs[k];
-    const int tr = pr.x < pr.y ? pr.x : pr.y, ts = pr.x < pr.y ? pr.y : pr.x;
-    {   // whole-tetrad spheres first: one test instead of 64 for the (typical) far-apart pair
+    unsigned long long m = 0;
+    if (k < p1) {
+        const int2 pr = pairs[k];
+        const int tr = pr.x < pr.y ? pr.x : pr.y, ts = pr.x < pr.y ? pr.y : pr.x;
         const double4* TB = reinterpret_cast<const double4*>(gb) + (size_t)n * 8;
         const double4 a = TB[tr], b = TB[ts];
         const double dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
         const double lim = a.w + b.w + dcut;
-        if (a.w < 0.0 || b.w < 0.0 || dx * dx + dy * dy + dz * dz > lim * lim * (1.0 + 1e-9)) { mask[k] = 0ull; return; }
-    }
-    const double4* R = reinterpret_cast<const double4*>(gb) + (size_t)tr * 8;
-    const double4* P = reinterpret_cast<const double4*>(gb) + (size_t)ts * 8;
-    double4 rr[8];
+        if (a.w >= 0.0 && b.w >= 0.0 && !(dx * dx + dy * dy + dz * dz > lim * lim * (1.0 + 1e-9))) {
+            const double4* R = reinterpret_cast<const double4*>(gb) + (size_t)tr * 8;
+            const double4* P = reinterpret_cast<const double4*>(gb) + (size_t)ts * 8;
+            double4 rr[8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) rr[r] = R[r];
-    unsigned long long m = 0;
+            for (int r = 0; r < 8; r++) rr[r] = R[r];
 #pragma unroll 1
-    for (int g = 0; g < 8; g++) {
-        const double4 q = P[g];
-        if (q.w < 0.0) continue;
+            for (int g = 0; g < 8; g++) {
+                const double4 q = P[g];
+                if (q.w < 0.0) continue;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const double dx = rr[r].x - q.x, dy = rr[r].y - q.y, dz = rr[r].z - q.z;
-            const double lim = rr[r].w + q.w + dcut;
-            if (rr[r].w >= 0.0 && dx * dx + dy * dy + dz * dz <= lim * lim * (1.0 + 1e-9)) m |= 1ull << (8 * g + r);
+                for (int r = 0; r < 8; r++) {
+                    const double ex = rr[r].x - q.x, ey = rr[r].y - q.y, ez = rr[r].z - q.z;
+                    const double l2 = rr[r].w + q.w + dcut;
+                    if (rr[r].w >= 0.0 && ex * ex + ey * ey + ez * ez <= l2 * l2 * (1.0 + 1e-9)) m |= 1ull << (8 * g + r);
+                }
+            }
         }
     }
-    mask[k] = m;
+    const unsigned live = __ballot_sync(0xffffffffu, m != 0ull);
+    if (!live) return;
+    const int lane = threadIdx.x & 31;
+    unsigned base = 0;
+    if (lane == __ffs(live) - 1) base = atomicAdd(count, (unsigned)__popc(live));
+    base = __shfl_sync(0xffffffffu, base, __ffs(live) - 1);
+    if (m) items[base + __popc(live & ((1u << lane) - 1u))] = CullItem{k, m};
 }
 
-__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_kernel(ScanArgs A, const unsigned long long* mask,
+__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_kernel(ScanArgs A, const CullItem* items,
+                                                                                    const unsigned* count,
                                                                                     const int* param_id, const int* perm) {
     constexpr double kBias = 16384.0;
     __shared__ __align__(16) double sb[4][kMaxStride + 2];
@@ -355,33 +371,39 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
     __shared__ __align__(8) unsigned long long bar;
     const int lane = threadIdx.x & 31;
     const int S = A.S;
-    const long long chunk = A.chunk;
-    const long long k0 = A.p0 + chunk * blockIdx.x;
-    const long long k1 = (k0 + chunk < A.p1) ? k0 + chunk : A.p1;
     const unsigned plane_bytes = 3u * (unsigned)S * 8u;
-
-    long long k = k0;
-    while (k < k1 && mask[k] == 0ull) k++;               // first pair with anything to do
-    if (k >= k1) return;
+    // The work list is cut into blocks of `chunk` items (one per lane, chunk <= 32), chunk chosen from
+    // the DEVICE-side item count so that a short list still spreads over every SM (one item per warp)
+    // and a long one amortises the register-side tetrad over a run of its partners.
+    const unsigned total = *count;
+    unsigned chunk = (total + (unsigned)A.chunk - 1) / (unsigned)A.chunk;     // A.chunk = blocks wanted (64 per SM)
+    chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+    if ((unsigned long long)blockIdx.x * chunk >= total) return;
 
     double xi[kTI], yi[kTI], zi[kTI];
     int hthr[kTI];
     double ox = 0.0, oy = 0.0, oz = 0.0;
     int cur_r = -1;
     bool wild = false;
-    int2 pr = A.pairs[k];
-    if (lane == 0) {
-        mbar_init(&bar, 1);
-        tma_load_1d(raw, A.crd + (size_t)(pr.x < pr.y ? pr.y : pr.x) * 3 * S, plane_bytes, &bar);
-    }
+    if (lane == 0) mbar_init(&bar, 1);
     __syncwarp();
     unsigned phase = 0;
-    while (k < k1) {
-        const unsigned long long m = mask[k];
-        long long kn = k + 1;
-        while (kn < k1 && mask[kn] == 0ull) kn++;
+    for (unsigned long long blk = blockIdx.x; blk * chunk < total; blk += gridDim.x) {
+    const unsigned i0 = (unsigned)(blk * chunk);
+    const unsigned i1 = (i0 + chunk < total) ? i0 + chunk : total;
+    CullItem mine{0, 0ull};
+    if (i0 + lane < i1) mine = items[i0 + lane];
+    const int nitems = (int)(i1 - i0);
+    int it = 0;
+    long long k = __shfl_sync(0xffffffffu, mine.k, 0);
+    int2 pr = A.pairs[k];
+    if (lane == 0) tma_load_1d(raw, A.crd + (size_t)(pr.x < pr.y ? pr.y : pr.x) * 3 * S, plane_bytes, &bar);
+    while (it < nitems) {
+        const unsigned long long m = __shfl_sync(0xffffffffu, mine.mask, it);
+        const bool more = it + 1 < nitems;
+        const long long kn = __shfl_sync(0xffffffffu, mine.k, more ? it + 1 : it);
         int2 pr_next = pr;
-        if (kn < k1) pr_next = A.pairs[kn];
+        if (more) pr_next = A.pairs[kn];
         const int tr = pr.x < pr.y ? pr.x : pr.y;
         const int tsc = pr.x < pr.y ? pr.y : pr.x;
         if (tr != cur_r) {
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
             }
         }
         __syncwarp();
-        if (lane == 0 && kn < k1) {
+        if (lane == 0 && more) {
             const int tsn = pr_next.x < pr_next.y ? pr_next.y : pr_next.x;
             tma_load_1d(raw, A.crd + (size_t)tsn * 3 * S, plane_bytes, &bar);
         }
@@ -451,28 +473,35 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
         if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);
         pr = pr_next;
         k = kn;
+        it++;
     }
+    }   // blocks of the work list
 }
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* mask, const int* param_id, const int* perm,
+                                unsigned long long* work, const int* param_id, const int* perm,
                                 unsigned char* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
+    // work buffer: [0] the item counter (16-byte slot), then one CullItem per listed pair at most
+    unsigned* count = reinterpret_cast<unsigned*>(work);
+    CullItem* items = reinterpret_cast<CullItem*>(work + 2);
+    cudaError_t err = cudaMemsetAsync(count, 0, 16, st);
+    if (err != cudaSuccess) return err;
     group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S);
     const long long want = p1 - p0;
-    pair_masks_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), mask, n);
-    long long chunk = want / ((long long)sms * 64);
-    if (chunk < 1) chunk = 1;
-    if (chunk > 16) chunk = 16;
-    const int grid = (int)((want + chunk - 1) / chunk);
+    pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
+    // The number of selected pairs is only known on the device: a fixed grid of up to 128 single-warp
+    // CTAs per SM walks the blocks of the list; CTAs beyond the list read the counter and exit.
+    const long long blocks_wanted = (long long)sms * 64;
+    const int grid = (int)(want < 2 * blocks_wanted ? want : 2 * blocks_wanted);
     long long bits; memcpy(&bits, &cut2_eff, 8);
-    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)chunk, cut2_eff, peers, world};
-    nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, mask, param_id, perm);
+    ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)blocks_wanted, cut2_eff, peers, world};
+    nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, items, count, param_id, perm);
     return cudaGetLastError();
 }
 
