@@ -45,6 +45,7 @@ struct Timer {
     double total_ms = 0.0;
     long long launches = 0;
     long long graph_launches = 0;   // kernel launches inside one replay of the step graph
+    unsigned char* d_need = nullptr; bool need_valid = false;   // [n] tetrad is an end of a pair in [p0,p1) (scan mode 4)
     double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
     double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
     cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
@@ -146,6 +147,7 @@ struct edmd_engine {
     Timer timers[T_COUNT];
     long long launches = 0;
     long long graph_launches = 0;   // kernel launches inside one replay of the step graph
+    unsigned char* d_need = nullptr; bool need_valid = false;   // [n] tetrad is an end of a pair in [p0,p1) (scan mode 4)
     double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
     double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
     cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
@@ -193,6 +195,7 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
     cudaFree(e->d_noise); e->d_noise = nullptr; e->noise_valid = false;
     cudaFree(e->d_pspre); e->d_pspre = nullptr;
+    cudaFree(e->d_need); e->d_need = nullptr; e->need_valid = false;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -299,6 +302,7 @@ void close_peers(edmd_engine* e) {
 unsigned char* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx[e->hit_parity] : e->d_hit; }
 
 void drop_graph(edmd_engine* e) {
+    e->need_valid = false;   // every caller changes the pair list, the shard or the scan mode
     if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
     e->graph_valid = false;
@@ -336,12 +340,22 @@ int do_ed(edmd_engine* e) {
     timer_end(e, T_ED, 2);
     return 0;
 }
+// which tetrads the culled distance pass needs bounding spheres for: the ends of this engine's pairs
+int ensure_need(edmd_engine* e) {
+    if (e->need_valid) return 0;
+    if (!e->d_need) CK(dev_alloc(&e->d_need, (size_t)e->n));
+    CK(launch_mark_needed(e->d_pairs, e->p0, e->p1, e->d_need, e->n, e->st));
+    e->launches++;
+    e->need_valid = true;
+    return 0;
+}
 int do_scan(edmd_engine* e) {
     const double cut_eff = nb_effective_cut2(e->sp);
     if (e->scan_mode == 4 && cut_eff >= 1e-3 && cut_eff < 1e6) {
+        if (int rc = ensure_need(e)) return rc;
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
-                               e->d_gb, e->d_pmask, e->d_param_id, e->d_perm,
+                               e->d_gb, e->d_pmask, e->d_param_id, e->d_perm, e->d_need,
                                e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -1106,6 +1120,7 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (!e->d_calls) CK(dev_alloc(&e->d_calls, 1));
     CK(cudaMemcpyAsync(e->d_calls, &e->calls, sizeof(long), cudaMemcpyHostToDevice, e->st));
     if (random_mode == 1) if (int rc = ensure_noise(e)) return rc;   // not inside the capture
+    if (e->scan_mode == 4) if (int rc = ensure_need(e)) return rc;
     if (!e->graph_valid || e->graph_random_mode != random_mode) {
         drop_graph(e);
         CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));

@@ -24,8 +24,9 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* mask, const int* param_id, const int* perm,
+                                unsigned long long* mask, const int* param_id, const int* perm, const unsigned char* need,
                                 unsigned char* const* peers, int world, cudaStream_t st);
+cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned char* hit, const long long* adj_off, const int* adj_partner,

@@ -269,12 +269,27 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 // group's 1-centre there (the atom of the average structure with the smallest maximum distance to
 // the rest of its group), so no centroid reduction is needed — and its radius is the largest
 // distance to that atom, reduced in FP32 with every conversion rounded UP (a bound, not an estimate).
-__global__ void __launch_bounds__(128) group_bounds_kernel(const double* crd, const int* natoms, const int* param_id,
-                                                            const int* perm, double* gb, int n, int S) {
+__global__ void mark_needed_kernel(const int2* pairs, long long p0, long long p1, unsigned char* need) {
+    const long long k = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= p1) return;
+    const int2 pr = pairs[k];
+    need[pr.x] = 1; need[pr.y] = 1;
+}
+cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st) {
+    cudaError_t err = cudaMemsetAsync(need, 0, (size_t)n, st);
+    if (err != cudaSuccess || p1 <= p0) return err;
+    mark_needed_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, st>>>(pairs, p0, p1, need);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd, const int* natoms, const int* param_id,
+                                                            const int* perm, double* gb, int n, int S,
+                                                            const unsigned char* need) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
+    if (!need[t]) return;        // not an end of any pair in this engine's scan slice (sharded runs)
     const double* X = crd + (size_t)t * 3 * S;
     const int* PM = perm + (size_t)param_id[t] * S;
     int a[8];
@@ -362,7 +377,7 @@ __global__ void __launch_bounds__(128) pair_select_kernel(const double* gb, cons
     if (m) items[base + __popc(live & ((1u << lane) - 1u))] = CullItem{k, m};
 }
 
-__global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_kernel(ScanArgs A, const CullItem* items,
+__global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs A, const CullItem* items,
                                                                                     const unsigned* count,
                                                                                     const int* param_id, const int* perm) {
     constexpr double kBias = 16384.0;
@@ -480,7 +495,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_cull_ker
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* work, const int* param_id, const int* perm,
+                                unsigned long long* work, const int* param_id, const int* perm, const unsigned char* need,
                                 unsigned char* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
@@ -492,7 +507,7 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     CullItem* items = reinterpret_cast<CullItem*>(work + 2);
     cudaError_t err = cudaMemsetAsync(count, 0, 16, st);
     if (err != cudaSuccess) return err;
-    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S);
+    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S, need);
     const long long want = p1 - p0;
     pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
     // The number of selected pairs is only known on the device: a fixed grid of up to 128 single-warp
