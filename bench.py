@@ -158,6 +158,8 @@ def run_reference(args, rank):
     npairs = N_TETRADS * (N_TETRADS - 1) // 2 - 5 * N_TETRADS
     vals, last = [], None
     per_step_budget = max(2.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    if args.ref_budget:
+        per_step_budget = args.ref_budget
     for it in range(args.warmup + args.steps):
         r = cpu_reference(s, npairs, per_step_budget)
         if it >= args.warmup:
@@ -183,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline sampling (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=0.0, help="--impl reference: seconds of CPU work per step (default: sized from --steps)")
     ap.add_argument("--no-scale-config", action="store_true", help="skip the 100,000-tetrad (C3) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -89,6 +89,11 @@ int  edmd_set_nb_clip(edmd_engine* e, int on);
  * provably hold no atom pair inside the cutoff.  The pass only selects tetrad pairs for the exact
  * FP64 force kernel, so forces and energies are bit-identical in all modes. */
 int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
+/* Projection kernel of the ED pass (edmd.cpp:106-150): 0 = automatic (default), 1 = one CTA per tetrad
+ * with the eigenvector coefficients in registers (any number of eigenvectors), 2 = one warp per
+ * tetrad with the parameter set staged in shared memory (sets with <= 12 eigenvectors; chosen
+ * automatically when tetrads share parameter sets).  Same arithmetic up to the order of one tree sum. */
+int  edmd_set_ed_kernel(edmd_engine* e, int which);
 
 /* ---- data in / out ----------------------------------------------------------------- */
 /* Replaces Master::send_Tetrads / Worker::recv_Tetrads (master.cpp:137-153, MPI_Tetrad

@@ -28,7 +28,6 @@
 //    Roofline: HBM — 96,872 algorithmic bytes per tetrad (SURVEY.md §8a a-ED); with
 //    de-duplicated parameter sets resident in L2 / shared memory the DRAM traffic drops to the
 //    24 KB of state.
-#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -653,14 +652,13 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
 
 cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                             cudaStream_t st) {
+                             bool use_warp_kernel, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
     superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return err;
-    static const bool force_cta = getenv("EDMD_ED_CTA") != nullptr;   // A/B switch for tools/probe_perf.py
-    if (ps.NEV <= kNevReg && !force_cta) {
+    if (use_warp_kernel && ps.NEV <= kNevReg) {
         const size_t smem = sizeof(double) * (kNevReg * 3 + 3) * ps.S;
         static bool configured = false;
         if (!configured) {

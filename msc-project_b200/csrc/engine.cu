@@ -134,6 +134,7 @@ struct edmd_engine {
     int rank = 1;
     long calls = 0;
 
+    int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
     bool use_graph = true, graph_valid = false;
@@ -335,8 +336,11 @@ int do_ed(edmd_engine* e) {
     timer_begin(e, T_ED);
     const double* src = e->latest_in_crd2 ? e->crd2 : e->crd;
     e->latest_in_crd2 = false;
+    // The warp-per-tetrad projection stages a parameter set in shared memory once per run of tetrads that
+    // share it: worth it when sets are shared (replicated DNA), not when every tetrad has its own.
+    const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && (long long)e->n >= 8LL * e->P);
     CK(launch_ed_forces(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
-                        e->t1 - e->t0, e->sp.scaled, e->st));
+                        e->t1 - e->t0, e->sp.scaled, warp, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -519,6 +523,14 @@ int edmd_set_nb_consts(edmd_engine* e, double krep, double qfac) {
 int edmd_set_nb_clip(edmd_engine* e, int on) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     e->nb_clip = on ? 1 : 0;
+    drop_graph(e);
+    return 0;
+}
+
+int edmd_set_ed_kernel(edmd_engine* e, int which) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    if (which < 0 || which > 2) return fail(EDMD_ERR_ARG, "ED kernel %d unknown (0 automatic, 1 thread per atom, 2 warp per tetrad)", which);
+    e->ed_kernel = which;
     drop_graph(e);
     return 0;
 }

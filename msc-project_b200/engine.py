@@ -72,6 +72,7 @@ def load_library():
         "edmd_set_nb_consts": (C.c_int, [E, C.c_double, C.c_double]),
         "edmd_set_nb_clip": (C.c_int, [E, C.c_int]),
         "edmd_set_nb_scan_mode": (C.c_int, [E, C.c_int]),
+        "edmd_set_ed_kernel": (C.c_int, [E, C.c_int]),
         "edmd_step_host": (C.c_int, [E, C.c_void_p, C.c_int, C.c_int, C.c_int]),
         "edmd_upload_tetrads": (C.c_int, [E, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
         "edmd_set_state": (C.c_int, [E, C.c_void_p, C.c_int]),
@@ -334,6 +335,9 @@ class Engine:
     # ---- the hot path -----------------------------------------------------------------
     def set_nb_consts(self, krep=100.0, qfac=0.0):
         self._ck(self.lib.edmd_set_nb_consts(self.h, krep, qfac))
+
+    def set_ed_kernel(self, which: int):
+        self._ck(self.lib.edmd_set_ed_kernel(self.h, which))
 
     def set_nb_scan_mode(self, mode: int):
         self._ck(self.lib.edmd_set_nb_scan_mode(self.h, mode))

@@ -206,3 +206,21 @@ def test_step_host_matches_the_three_separate_calls(edmd, ragged):
         a.merge(); b.merge()                                        # the device state is consistent afterwards
         (ca, va), (cb, vb) = a.get_state(), b.get_state()
         assert np.array_equal(ca, cb) and np.array_equal(va, vb)
+
+
+def test_both_projection_kernels_match_the_oracle(edmd, po):
+    """ED pass with the thread-per-atom projection (edmd_set_ed_kernel(1)) and with the warp-per-tetrad
+    projection (2) on a system whose tetrads share two parameter sets and on one where every tetrad has
+    its own: both within the parity bound of the CPU oracle, and equal to each other up to the order of
+    the 12 projection sums."""
+    for s in (edmd.make_ring(120, kind="coil", laps=3, lap_gap=9.0), edmd.make_gc90()):
+        o = po.Oracle(s, "port"); o.build_pairs(); o.forces(random_on=False)
+        fo = o.get_forces(); co, _ = o.get_state()
+        out = []
+        for which in (1, 2, 0):
+            g = edmd.Engine(s); g.set_ed_kernel(which); g.build_pairlist(); g.ed_forces()
+            fg = g.get_forces(); cg, _ = g.get_state()
+            assert rel(fg["ed"], fo["ed"]) < TOL and rel(fg["ed_energy"], fo["ed_energy"]) < TOL
+            assert rel(cg, co) < TOL
+            out.append((fg["ed"], cg))
+        assert rel(out[0][0], out[1][0]) < 1e-12 and rel(out[0][1], out[1][1]) < 1e-13
