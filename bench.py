@@ -466,7 +466,7 @@ def main():
             "kernel_ms": kern,
             "variants": variants,
             "scale_config": c3,
-            "roofline": {"kernel": "NB distance pass: group_bounds + pair_masks + nb_scan_cull_kernel (engine default)",
+            "roofline": {"kernel": "NB distance pass: group_bounds + pair_select + nb_scan_cull_kernel (engine default)",
                          "bound": "fp64", "achieved": achieved,
                          "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                          "traffic": traffic,

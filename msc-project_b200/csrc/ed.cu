@@ -660,7 +660,12 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
     if (err != cudaSuccess) return err;
     if (use_warp_kernel && ps.NEV <= kNevReg) {
         const size_t smem = sizeof(double) * (kNevReg * 3 + 3) * ps.S;
-        static bool configured = false;
+        // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it
+        static bool done[64] = {};
+        int dev = 0;
+        err = cudaGetDevice(&dev);
+        if (err != cudaSuccess) return err;
+        bool& configured = done[dev & 63];
         if (!configured) {
             const int most = (int)(sizeof(double) * (kNevReg * 3 + 3) * kMaxStride);
             err = cudaFuncSetAttribute(ed_project_warp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);

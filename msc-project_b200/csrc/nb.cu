@@ -254,21 +254,20 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
 
 // ---- MODE 4: gram form + bounding-sphere culling ---------------------------------------------------
 // The 256 slots of a tetrad are filled with its atoms through a per-parameter-set permutation that
-// makes slots 32g .. 32g+31 a spatially compact group g (recursive coordinate bisection of the average
-// structure, engine.cu); in the register tile group r is exactly register r.  group_bounds_kernel gives every group a bounding sphere; pair_masks_kernel turns the
-// 8 x 8 sphere tests of a tetrad pair into a 64-bit mask (bit 8g + r: register group r may be within
-// sqrt(cut) of partner group g); the scan then skips whole pairs (mask 0: no TMA, no staging) and,
-// inside a pair, every (register group, partner group) block whose spheres are too far apart.
-// Conservative by construction (spheres contain their atoms, the test is inflated by 1e-9), so the
-// selected pairs remain a superset of the true hits and the final forces are bit-identical.
-// A pair of whole-tetrad spheres is tested first, so the typical far-apart listed pair costs one
-// sphere test.  Results are bit-identical to the brute-force modes (tests/test_gpu_edge.py), so
-// this is the engine's default; modes 0-2 evaluate all 63,504 atom pairs of every listed pair
-// and are kept for the roofline measurement of the distance kernel (bench.py `variants`).
-// One warp per tetrad.  Group g's sphere is centred on the atom in its slot 0 — the upload puts the
-// group's 1-centre there (the atom of the average structure with the smallest maximum distance to
-// the rest of its group), so no centroid reduction is needed — and its radius is the largest
-// distance to that atom, reduced in FP32 with every conversion rounded UP (a bound, not an estimate).
+// makes slots 32g .. 32g+31 a spatially compact group g (recursive coordinate bisection of the
+// average structure, engine.cu); in the register tile group r is exactly register r.
+//   group_bounds_kernel   a bounding sphere for every group and for every whole tetrad that is an
+//                         end of one of this engine's pairs (mark_needed_kernel);
+//   pair_select_kernel    one tetrad-sphere test per listed pair, then the 8 x 8 group-sphere tests
+//                         -> a 64-bit mask (bit 8g + r: register group r may be within sqrt(cut) of
+//                         partner group g); pairs with a non-empty mask go to a compact work list;
+//   nb_scan_cull_kernel   walks the work list: TMA-loads the partner, stages it in group order and
+//                         evaluates only the masked 32 x 32 blocks with the gram arithmetic of MODE 1.
+// Conservative by construction (spheres contain their atoms, every test is inflated), so the selected
+// pairs remain a superset of the true hits and the final forces are bit-identical to modes 0-2
+// (tests/test_gpu_edge.py).  This is the engine's default; modes 0-2 evaluate all 63,504 atom pairs
+// of every listed pair like the reference does and are kept for the roofline measurement of the
+// distance kernel (bench.py `variants`).
 __global__ void mark_needed_kernel(const int2* pairs, long long p0, long long p1, unsigned char* need) {
     const long long k = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= p1) return;
