@@ -42,3 +42,27 @@ def test_gpu_arm_has_no_cpu_fallback():
         pytest.skip("a CUDA device is present")
     r = run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_clock_sampler_parses_nvidia_smi_lines():
+    """The `clocks` object: median SM clock and throttle reasons of the samples inside the timed region,
+    falling back to every sample of the run when the region is shorter than a few sampling periods."""
+    sys.path.insert(0, ROOT)
+    import importlib, time, datetime
+    bench = importlib.import_module("bench")
+    cs = bench.ClockSampler(0)
+    cs.proc = type("P", (), {"terminate": lambda s: None, "wait": lambda s, timeout=None: 0, "kill": lambda s: None})()
+    now = time.time()
+
+    def line(dt, mhz, power_cap="Not Active", hw="Not Active"):
+        ts = datetime.datetime.fromtimestamp(now + dt).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+        return f"{ts}, {mhz}, 1965, 600.0, 0x0, {hw}, Not Active, Not Active, {power_cap}"
+    cs.lines = [line(-1.0, 1200), line(0.1, 1965), line(0.2, 1950, power_cap="Active"), line(0.3, 1965), line(2.0, 900, hw="Active"),
+                "garbage line", "2026/01/01 00:00:00.000, [N/A], [N/A], x, x, x, x, x, x"]
+    cs.t_begin, cs.t_end = now, now + 0.4
+    c = cs.stop()
+    assert c["window"] == "timed region" and c["samples"] == 3 and c["sm_mhz"] == 1965 and c["sm_max_mhz"] == 1965
+    assert c["reasons"] == ["sw_power_cap"]
+    cs.t_begin, cs.t_end = now + 0.15, now + 0.16            # a 10 ms region: only one sample inside
+    c = cs.stop()
+    assert c["window"].startswith("whole run") and c["samples"] == 5 and "hw_slowdown" in c["reasons"]
