@@ -1131,10 +1131,12 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (random_mode == 0) { if (int rc = do_random(e, 0, 0, 0, 0)) return rc; }
     if (!e->d_calls) CK(dev_alloc(&e->d_calls, 1));
     CK(cudaMemcpyAsync(e->d_calls, &e->calls, sizeof(long), cudaMemcpyHostToDevice, e->st));
-    if (random_mode == 1) if (int rc = ensure_noise(e)) return rc;   // not inside the capture
-    if (e->scan_mode == 4) if (int rc = ensure_need(e)) return rc;
     if (!e->graph_valid || e->graph_random_mode != random_mode) {
         drop_graph(e);
+        // tables that depend only on the parameters / the pair slice: built here, NOT inside the capture
+        // (drop_graph has just invalidated the second one)
+        if (random_mode == 1) if (int rc = ensure_noise(e)) return rc;
+        if (e->scan_mode == 4) if (int rc = ensure_need(e)) return rc;
         CK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
         const bool zero_flag = e->rnd_zero;
         const long long counted = e->launches;
