@@ -159,7 +159,7 @@ def test_trajectory(edmd, po, coil, random_on):
         (co, vo), (cg, vg) = o.get_state(), g.get_state()
         worst = max(worst, rel(cg, co), rel(vg, vo))
     # The 60-tetrad double coil is deliberately violent (interpenetrating helices, forces at the
-    # clip, stiff soft-core); measured growth: 1e-12 after 10 steps (tools/probe_growth.py).
+    # clip, stiff soft-core); measured growth: 1e-12 after 10 steps (tests/tools/probe_growth.py).
     assert worst < TOL
     o.merge(); g.merge()
     assert rel(g.get_state()[0], o.get_state()[0]) < TOL

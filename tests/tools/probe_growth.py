@@ -1,6 +1,7 @@
-"""Error growth of the GPU trajectory against the CPU oracle, step by step."""
+"""Error growth of the GPU trajectory against the CPU oracle, step by step (test tooling: the only
+places that may use oracle/ are tests/, smoke() and bench.py's CPU baseline)."""
 import importlib, os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import pyoracle as po
