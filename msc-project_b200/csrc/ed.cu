@@ -33,6 +33,33 @@
 
 namespace edmd {
 
+// ---- QCP rotation ---------------------------------------------------------------------------------
+// qcp_rotation below restates, expression for expression (bit-identical rotation matrices are the
+// contract), the closed-form algebra of FastCalcRMSDAndRotation in the QCP reference implementation
+// qcprot.c v1.4, which carries this notice:
+//
+//   Copyright (c) 2009-2013 Pu Liu and Douglas L. Theobald.  All rights reserved.
+//   Redistribution and use in source and binary forms, with or without modification, are permitted
+//   provided that the following conditions are met:
+//   * Redistributions of source code must retain the above copyright notice, this list of conditions
+//     and the following disclaimer.
+//   * Redistributions in binary form must reproduce the above copyright notice, this list of
+//     conditions and the following disclaimer in the documentation and/or other materials provided
+//     with the distribution.
+//   * Neither the name of the <ORGANIZATION> nor the names of its contributors may be used to endorse
+//     or promote products derived from this software without specific prior written permission.
+//   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR
+//   IMPLIED WARRANTIES, INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND
+//   FITNESS FOR A PARTICULAR PURPOSE ARE DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT HOLDER OR
+//   CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL, SPECIAL, EXEMPLARY, OR CONSEQUENTIAL
+//   DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR SERVICES; LOSS OF USE,
+//   DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY, WHETHER
+//   IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF
+//   THE USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
+//
+//   Method: D. L. Theobald (2005) Acta Cryst. A 61(4):478-480; P. Liu, D. K. Agrafiotis and
+//   D. L. Theobald (2009) J. Comput. Chem. 31(7):1561-1563.
+//
 // Rotation from the 3x3 cross-covariance M (row-major, ref (x) mov) and e0 = (G_ref+G_mov)/2:
 // largest root of the QCP quartic by Newton from e0 (stop |dl| < 1e-11 |l|, <= 50 iterations),
 // quaternion = a non-vanishing column of adj(K - l I) (norm^2 >= 1e-6, else next column, else

@@ -44,12 +44,6 @@ struct Timer {
     std::vector<cudaEvent_t> ev;   // start/stop pairs not yet folded
     double total_ms = 0.0;
     long long launches = 0;
-    long long graph_launches = 0;   // kernel launches inside one replay of the step graph
-    unsigned char* d_need = nullptr; bool need_valid = false;   // [n] tetrad is an end of a pair in [p0,p1) (scan mode 4)
-    double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
-    double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
-    cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
-    cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
 };
 
 template <class T>
@@ -84,11 +78,13 @@ struct edmd_engine {
     double* crd2 = nullptr;        // post-integrate coordinates written by the fused finish kernel
     bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
-    unsigned char *d_mark = nullptr, *d_dirty = nullptr;
+    int* d_mark = nullptr;            // [2n+1] per-tetrad "in a flagged pair" flags, list counter, list of marked tetrads
+    unsigned char* d_dirty = nullptr; // [n] fnb of this tetrad is non-zero from an earlier step
     double* d_gb = nullptr;                 // [n][8][4] group + [n][4] tetrad bounding spheres (scan mode 4)
-    int* d_perm = nullptr;                  // [P][S] slot -> atom, compact groups of 32 (scan mode 4)
+    int* d_perm = nullptr;                  // [P][kMaxStride] slot -> atom, compact groups of 32 (culling scan, force pass)
+    unsigned long long* d_grp = nullptr;    // [P][32] atom -> slot group, byte c of entry l = group of atom 32c+l
     unsigned long long* d_pmask = nullptr;  // counter + [pairs_cap] {pair index, 8x8 group mask} work items (scan mode 4)
-    long long pmask_cap = 0;   // per-tetrad: in a flagged pair now / fnb non-zero
+    long long pmask_cap = 0;
     bool rnd_zero = true;   // random terms currently all zero
 
     // staging (interleaved flat), 3 slots
@@ -98,7 +94,7 @@ struct edmd_engine {
     // pair list + adjacency
     int2* d_pairs = nullptr;
     long long np = 0, pairs_cap = 0;
-    unsigned char* d_hit = nullptr;
+    unsigned long long* d_hit = nullptr;   // [pairs_cap] per-pair block masks of the distance pass (0 = not flagged)
     long long *d_row_count = nullptr, *d_row_off = nullptr, *d_adj_off = nullptr;
     int *d_adj_partner = nullptr, *d_adj_pair = nullptr;
     long long adj_cap = 0;
@@ -113,9 +109,9 @@ struct edmd_engine {
 
     // peer-shared hit flags (fused scan + broadcast over NVLink): two buffers used by step parity,
     // exported with CUDA IPC; peer_tbl[b][r] = rank r's buffer b as mapped into this process
-    unsigned char* d_hitx[2] = {nullptr, nullptr};
+    unsigned long long* d_hitx[2] = {nullptr, nullptr};
     long long hitx_cap = 0;
-    unsigned char** d_peer_tbl = nullptr;   // device array [2][world]
+    unsigned long long** d_peer_tbl = nullptr;   // device array [2][world]
     std::vector<void*> peer_opened;
     int world = 1, rank_id = 0, hit_parity = 0;
     bool peer_mode = false;
@@ -191,8 +187,9 @@ void free_system(edmd_engine* e) {
     close_peers(e);
     cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
     cudaFree(e->d_calls); e->d_calls = nullptr;
-    cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = e->d_dirty = nullptr;
+    cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = nullptr; e->d_dirty = nullptr;
     cudaFree(e->d_perm); e->d_perm = nullptr;
+    cudaFree(e->d_grp); e->d_grp = nullptr;
     cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
     cudaFree(e->d_noise); e->d_noise = nullptr; e->noise_valid = false;
     cudaFree(e->d_pspre); e->d_pspre = nullptr;
@@ -300,7 +297,7 @@ void close_peers(edmd_engine* e) {
     e->peer_mode = false;
 }
 
-unsigned char* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx[e->hit_parity] : e->d_hit; }
+unsigned long long* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx[e->hit_parity] : e->d_hit; }
 
 void drop_graph(edmd_engine* e) {
     e->need_valid = false;   // every caller changes the pair list, the shard or the scan mode
@@ -373,32 +370,31 @@ int do_scan(edmd_engine* e) {
     e->hits_valid = true;
     return 0;
 }
-int do_accumulate(edmd_engine* e, int use_hits) {
+int do_accumulate(edmd_engine* e) {
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)e->n, e->st));
     timer_begin(e, T_ACC);
     CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_adj_off,
-                            e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->t0, e->t1 - e->t0, e->S,
-                            e->sp, use_hits, e->nb_clip, e->st));
+                            e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->t0,
+                            e->t1 - e->t0, e->S, e->sp, e->nb_clip, e->st));
     timer_end(e, T_ACC, 1);
     return 0;
 }
 // accumulate + clip + velocity + coordinate update in one kernel (edmd_step, edmd_nb_finish)
-int do_accumulate(edmd_engine* e, int use_hits);
 int do_integrate(edmd_engine* e, int do_vel, int do_crd);
 int do_finish(edmd_engine* e) {
     if (int rc = normalize(e)) return rc;
     if (!e->nb_clip) {   // unclipped forces requested: run the two unfused kernels
-        if (int rc = do_accumulate(e, 1)) return rc;
+        if (int rc = do_accumulate(e)) return rc;
         return do_integrate(e, 1, 1);
     }
     timer_begin(e, T_ACC);
     CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
-                              e->d_adj_partner, e->d_adj_pair, e->fnb, e->e_nb, e->ps, e->vel, e->crd2, e->fed,
-                              e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n, e->t0,
-                              e->t1 - e->t0, e->S, e->sp, e->st));
+                              e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->ps, e->vel,
+                              e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n,
+                              e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
     timer_end(e, T_ACC, 3);
     if (e->peer_mode) {   // this buffer is written again by the peers' scans two steps from now
-        CK(cudaMemsetAsync(e->d_hitx[e->hit_parity], 0, (size_t)e->np, e->st));
+        CK(cudaMemsetAsync(e->d_hitx[e->hit_parity], 0, sizeof(unsigned long long) * (size_t)e->np, e->st));
         e->hit_parity ^= 1;
     }
     e->latest_in_crd2 = true;
@@ -617,9 +613,10 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
         }
     }
 
-    // slot permutation for the culling scan: recursive coordinate bisection of each average structure
-    // into 8 groups of <= 32 atoms (slots 32g..32g+31), padded with -1
-    std::vector<int> perm((size_t)P * S, -1);
+    // slot permutation for the culling scan and the force pass: recursive coordinate bisection of each
+    // average structure into 8 groups of <= 32 atoms (slots 32g..32g+31 of kMaxStride = 256 slots, whatever
+    // the atom stride S is), padded with -1
+    std::vector<int> perm((size_t)P * kMaxStride, -1);
     for (int p = 0; p < P; p++) {
         const edmd_tetrad& T = tets[rep[p]];
         std::vector<int> idx(T.num_Atoms);
@@ -643,7 +640,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
                     if (r2 < best_r) { best_r = r2; best = q; }
                 }
                 if (j.hi > j.lo) std::swap(idx[j.lo], idx[best]);
-                for (int q = j.lo; q < j.hi && q - j.lo < 32; q++) perm[(size_t)p * S + 32 * j.first + (q - j.lo)] = idx[q];
+                for (int q = j.lo; q < j.hi && q - j.lo < 32; q++) perm[(size_t)p * kMaxStride + 32 * j.first + (q - j.lo)] = idx[q];
                 continue;
             }
             double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
@@ -661,8 +658,20 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
             jobs.push_back({j.lo + left, j.hi, half, j.first + half});
         }
     }
+    // inverse table for the force pass: slot group of every atom, eight atoms (32c + l, c = 0..7) per word
+    std::vector<unsigned long long> grp((size_t)P * 32, ~0ull);
+    for (int p = 0; p < P; p++)
+        for (int slot = 0; slot < kMaxStride; slot++) {
+            const int a = perm[(size_t)p * kMaxStride + slot];
+            if (a < 0) continue;
+            unsigned long long& wd = grp[(size_t)p * 32 + (a & 31)];
+            const int sh = 8 * (a >> 5);
+            wd = (wd & ~(0xffull << sh)) | ((unsigned long long)(slot >> 5) << sh);
+        }
     CK(dev_alloc(&e->d_perm, perm.size()));
     CK(cudaMemcpyAsync(e->d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, e->st));
+    CK(dev_alloc(&e->d_grp, grp.size()));
+    CK(cudaMemcpyAsync(e->d_grp, grp.data(), sizeof(unsigned long long) * grp.size(), cudaMemcpyHostToDevice, e->st));
     CK(dev_alloc(&e->d_natoms, n)); CK(dev_alloc(&e->d_param_id, n)); CK(dev_alloc(&e->d_off3, n + 1));
     CK(dev_alloc(&e->d_ps_na, P)); CK(dev_alloc(&e->d_ps_nev, P));
     CK(dev_alloc(&e->d_avg, avg.size())); CK(dev_alloc(&e->d_mass, mass.size())); CK(dev_alloc(&e->d_chg, chg.size()));
@@ -672,7 +681,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
     CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
-    CK(dev_alloc(&e->d_mark, (size_t)n)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 2)); CK(dev_alloc(&e->d_dirty, (size_t)n));
     CK(dev_alloc(&e->d_gb, (size_t)n * 36));
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)n, e->st));   // unknown force contents: treat as dirty
     CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
@@ -1015,7 +1024,7 @@ int edmd_nb_accumulate(edmd_engine* e) {
     if (int rc = check_ready(e, true)) return rc;
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
-    return do_accumulate(e, 1);
+    return do_accumulate(e);
 }
 
 int edmd_nb_forces(edmd_engine* e) {
@@ -1023,7 +1032,7 @@ int edmd_nb_forces(edmd_engine* e) {
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
     if (int rc = do_scan(e)) return rc;
-    return do_accumulate(e, 1);
+    return do_accumulate(e);
 }
 
 int edmd_update_velocities(edmd_engine* e) {
@@ -1223,7 +1232,7 @@ int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes) {
         case EDMD_BUF_FED: p = e->fed; b = planes; break;
         case EDMD_BUF_RND: p = e->rnd; b = planes; break;
         case EDMD_BUF_FNB: p = e->fnb; b = planes; break;
-        case EDMD_BUF_HIT: p = cur_hits(e); b = (size_t)e->np; break;
+        case EDMD_BUF_HIT: p = cur_hits(e); b = sizeof(unsigned long long) * (size_t)e->np; break;
         case EDMD_BUF_CENTROID: p = e->cen; b = sizeof(double) * 4 * (size_t)e->n; break;
         default: return fail(EDMD_ERR_ARG, "unknown buffer %d", which);
     }
@@ -1297,12 +1306,40 @@ long long edmd_launch_count(edmd_engine* e) { return e ? e->launches : 0; }
 int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs) {
     if (int rc = check_ready(e, true)) return rc;
     CK(cudaSetDevice(e->device));
-    std::vector<unsigned char> h((size_t)e->np);
+    std::vector<unsigned long long> h((size_t)e->np);
     CK(cudaStreamSynchronize(e->st));
-    if (e->np) CK(cudaMemcpy(h.data(), cur_hits(e), (size_t)e->np, cudaMemcpyDeviceToHost));
+    if (e->np) CK(cudaMemcpy(h.data(), cur_hits(e), sizeof(unsigned long long) * (size_t)e->np, cudaMemcpyDeviceToHost));
     long long c = 0;
     for (long long p = e->p0; p < e->p1; p++) c += h[p] != 0;
     if (flagged_pairs) *flagged_pairs = c;
+    return 0;
+}
+
+int edmd_nb_stats_ex(edmd_engine* e, long long out[4]) {
+    if (int rc = check_ready(e, true)) return rc;
+    if (!out) return fail(EDMD_ERR_ARG, "null output");
+    CK(cudaSetDevice(e->device));
+    std::vector<unsigned long long> h((size_t)e->np);
+    std::vector<int2> pr((size_t)e->np);
+    CK(cudaStreamSynchronize(e->st));
+    if (e->np) {
+        CK(cudaMemcpy(h.data(), cur_hits(e), sizeof(unsigned long long) * (size_t)e->np, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(pr.data(), e->d_pairs, sizeof(int2) * (size_t)e->np, cudaMemcpyDeviceToHost));
+    }
+    std::vector<unsigned char> marked((size_t)e->n, 0);
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (long long p = 0; p < e->np; p++) {
+        if (!h[p]) continue;
+        out[0]++;
+        out[2] += __builtin_popcountll(h[p]);
+        marked[pr[p].x] = 1; marked[pr[p].y] = 1;
+    }
+    for (int t = e->t0; t < e->t1; t++) out[1] += marked[t];
+    if (e->scan_mode == 4 && e->d_pmask) {
+        unsigned cnt = 0;
+        CK(cudaMemcpy(&cnt, e->d_pmask, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        out[3] = cnt;
+    }
     return 0;
 }
 
@@ -1323,12 +1360,12 @@ int edmd_peer_hits_export(edmd_engine* e, unsigned char* handles /* 2 x 64 bytes
     if (need > e->hitx_cap) {
         cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
         const long long cap = need + need / 2 + 4096;
-        CK(cudaMalloc((void**)&e->d_hitx[0], (size_t)cap)); CK(cudaMalloc((void**)&e->d_hitx[1], (size_t)cap));
+        CK(cudaMalloc((void**)&e->d_hitx[0], sizeof(unsigned long long) * (size_t)cap)); CK(cudaMalloc((void**)&e->d_hitx[1], sizeof(unsigned long long) * (size_t)cap));
         e->hitx_cap = cap;
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     for (int b = 0; b < 2; b++) {
-        CK(cudaMemset(e->d_hitx[b], 0, (size_t)e->hitx_cap));
+        CK(cudaMemset(e->d_hitx[b], 0, sizeof(unsigned long long) * (size_t)e->hitx_cap));
         cudaIpcMemHandle_t h;
         CK(cudaIpcGetMemHandle(&h, e->d_hitx[b]));
         memcpy(handles + 64 * b, &h, 64);
@@ -1342,7 +1379,7 @@ int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* worl
         return fail(EDMD_ERR_ARG, "edmd_peer_hits_open: bad arguments (export first; world <= 32)");
     CK(cudaSetDevice(e->device));
     close_peers(e);
-    std::vector<unsigned char*> tbl(2 * (size_t)world, nullptr);
+    std::vector<unsigned long long*> tbl(2 * (size_t)world, nullptr);
     for (int r = 0; r < world; r++)
         for (int b = 0; b < 2; b++) {
             if (r == rank) { tbl[(size_t)b * world + r] = e->d_hitx[b]; continue; }
@@ -1351,10 +1388,10 @@ int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* worl
             void* p = nullptr;
             CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
             e->peer_opened.push_back(p);
-            tbl[(size_t)b * world + r] = (unsigned char*)p;
+            tbl[(size_t)b * world + r] = (unsigned long long*)p;
         }
-    CK(cudaMalloc((void**)&e->d_peer_tbl, sizeof(unsigned char*) * tbl.size()));
-    CK(cudaMemcpy(e->d_peer_tbl, tbl.data(), sizeof(unsigned char*) * tbl.size(), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&e->d_peer_tbl, sizeof(unsigned long long*) * tbl.size()));
+    CK(cudaMemcpy(e->d_peer_tbl, tbl.data(), sizeof(unsigned long long*) * tbl.size(), cudaMemcpyHostToDevice));
     e->world = world; e->rank_id = rank; e->hit_parity = 0; e->peer_mode = true;
     drop_graph(e);
     return 0;

@@ -18,33 +18,31 @@ cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const dou
                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                              bool use_warp_kernel, cudaStream_t st);
 
-cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
+cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                            long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
-                           unsigned char* const* peers, int world, cudaStream_t st);
+                           unsigned long long* const* peers, int world, cudaStream_t st);
 
-cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
+cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* mask, const int* param_id, const int* perm, const unsigned char* need,
-                                unsigned char* const* peers, int world, cudaStream_t st);
+                                unsigned long long* const* peers, int world, cudaStream_t st);
 cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
+// hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the
+// per-parameter-set slot -> atom and atom -> slot-group tables the masks refer to (engine.cu)
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
-                                 const unsigned char* hit, const long long* adj_off, const int* adj_partner,
-                                 const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
-                                 const SimParams& sp, int use_hits, int clip, cudaStream_t st);
+                                 const unsigned long long* hit, const long long* adj_off, const int* adj_partner,
+                                 const int* adj_pair, const int* perm, const unsigned long long* grp, double* fnb,
+                                 double* e_nb, int t0, int count, int S, const SimParams& sp, int clip, cudaStream_t st);
 
-cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
-                             const unsigned char* hit, const long long* adj_off, const int* adj_partner,
-                             const int* adj_pair, double* fnb, double* e_nb, const ParamSets& ps, double* vel,
-                             double* crd_out, const double* fed, const double* rnd, double* temp, int t0, int count,
-                             int S, const SimParams& sp, cudaStream_t st);
-
+// mark: int [2n + 1] scratch (flags, list counter, compact list of marked tetrads)
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
-                                   const unsigned char* hit, const int2* pairs, long long np, const long long* adj_off,
-                                   const int* adj_partner, const int* adj_pair, double* fnb, double* e_nb,
+                                   const unsigned long long* hit, const int2* pairs, long long np, const long long* adj_off,
+                                   const int* adj_partner, const int* adj_pair, const int* perm,
+                                   const unsigned long long* grp, double* fnb, double* e_nb,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
-                                   const double* rnd, double* temp, unsigned char* mark, unsigned char* dirty, int n,
-                                   int t0, int count, int S, const SimParams& sp, cudaStream_t st);
+                                   const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
+                                   int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st);
 
 cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
                              const double* fed, const double* rnd, const double* fnb, double* temp,

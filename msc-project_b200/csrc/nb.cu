@@ -40,7 +40,7 @@ struct ScanArgs {
     const double* crd;      // [n][3][S]
     const int* natoms;      // [n] atoms per tetrad
     const int2* pairs;      // [np] (t1, t2)
-    unsigned char* hit;     // [np], zeroed before the launch; set to 1 by any warp that sees a hit
+    unsigned long long* hit;   // [np] per-pair 8 x 8 block masks, zeroed before the launch; non-zero = the pair is flagged
     long long p0, p1;       // this launch covers pairs [p0, p1)
     int S;
     int hi_cut;             // high word of the effective squared cutoff (MODE 0)
@@ -48,13 +48,16 @@ struct ScanArgs {
     double cut;             // effective squared cutoff (MODE 1)
     // Fused compute + collective: when `peers` is set, a hit is stored straight into the hit buffer of
     // EVERY rank (peer pointers over NVLink/NVSwitch, CUDA IPC) instead of being all-gathered later.
-    unsigned char* const* peers;   // [world] device pointers, this rank's own buffer included
+    unsigned long long* const* peers;   // [world] device pointers, this rank's own buffer included
     int world;
 };
 
-__device__ __forceinline__ void publish_hit(const ScanArgs& A, long long k, int lane) {
-    if (A.peers) { if (lane < A.world) A.peers[lane][k] = 1; }
-    else if (lane == 0) A.hit[k] = 1;
+// mask: which 32 x 32 atom blocks of the pair may hold an atom pair inside the cutoff (bit 8g + r: slot
+// group r of the lower-numbered tetrad against slot group g of the higher-numbered one); the brute-force
+// modes do not track blocks and publish all ones.
+__device__ __forceinline__ void publish_hit(const ScanArgs& A, long long k, int lane, unsigned long long mask) {
+    if (A.peers) { if (lane < A.world) A.peers[lane][k] = mask; }
+    else if (lane == 0) A.hit[k] = mask;
 }
 
 constexpr int kScanThreads = 32;                       // one warp = one CTA = one tetrad pair at a time
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(kScanThreads, kScanCtasPerSm) nb_scan_kernel(S
         } else {
             pred = min(mm[0], mm[1]) <= A.hi_cut;
         }
-        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);   // (the vote is also the WAR fence of the single buffer)
+        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane, ~0ull);   // (the vote is also the WAR fence of the single buffer)
         pr = pr_next;
     }
 }
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd
     if (t >= n) return;
     if (!need[t]) return;        // not an end of any pair in this engine's scan slice (sharded runs)
     const double* X = crd + (size_t)t * 3 * S;
-    const int* PM = perm + (size_t)param_id[t] * S;
+    const int* PM = perm + (size_t)param_id[t] * kMaxStride;
     int a[8];
 #pragma unroll
     for (int g = 0; g < 8; g++) a[g] = PM[32 * g + lane];     // slot -> atom, -1 = empty slot
@@ -318,16 +321,15 @@ __global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd
         tx += __shfl_xor_sync(full, tx, o); ty += __shfl_xor_sync(full, ty, o);
         tz += __shfl_xor_sync(full, tz, o); tn += __shfl_xor_sync(full, tn, o);
     }
-    double trad = -1.0;
-    if (tn > 0) {
-        const double inv = (double)__frcp_rn((float)tn);       // any centre will do: the radius is measured from it
-        tx *= inv; ty *= inv; tz *= inv;
-        const double dd = (gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz);
-        float reach = have ? __fadd_ru(__fsqrt_ru(__double2float_ru(dd)), __double2float_ru(gr)) : 0.0f;
+    // (every lane runs the shuffles below: tn is non-zero in lanes 0..7 only, and a shuffle inside a
+    // branch that part of the named lanes skip is undefined)
+    const double inv = tn > 0 ? (double)__frcp_rn((float)tn) : 0.0;   // any centre will do: the radius is measured from it
+    tx *= inv; ty *= inv; tz *= inv;
+    const double dd = (gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz);
+    float reach = have ? __fadd_ru(__fsqrt_ru(__double2float_ru(dd)), __double2float_ru(gr)) : 0.0f;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) reach = fmaxf(reach, __shfl_xor_sync(full, reach, o));
-        trad = (double)reach * (1.0 + 1e-12) + 1e-12;
-    }
+    for (int o = 4; o > 0; o >>= 1) reach = fmaxf(reach, __shfl_xor_sync(full, reach, o));
+    const double trad = tn > 0 ? (double)reach * (1.0 + 1e-12) + 1e-12 : -1.0;
     if (lane == 0) *reinterpret_cast<double4*>(gb + (size_t)n * 32 + (size_t)t * 4) = make_double4(tx, ty, tz, trad);
 }
 
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
         if (tr != cur_r) {
             cur_r = tr;
             const double* Xr = A.crd + (size_t)tr * 3 * S;
-            const int* PR = perm + (size_t)param_id[tr] * S;
+            const int* PR = perm + (size_t)param_id[tr] * kMaxStride;
             ox = Xr[0]; oy = Xr[S]; oz = Xr[2 * S]; wild = false;
 #pragma unroll
             for (int r = 0; r < kTI; r++) {
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
         mbar_wait(&bar, phase);
         phase ^= 1;
         {   // stage all 256 slots of the partner in its own compact-group order (empty slots never hit)
-            const int* PS = perm + (size_t)param_id[tsc] * S;
+            const int* PS = perm + (size_t)param_id[tsc] * kMaxStride;
 #pragma unroll
             for (int r = 0; r < kTI; r++) {
                 const int slot = lane + kScanThreads * r;
@@ -456,14 +458,18 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
             const int tsn = pr_next.x < pr_next.y ? pr_next.y : pr_next.x;
             tma_load_1d(raw, A.crd + (size_t)tsn * 3 * S, plane_bytes, &bar);
         }
-        int mm[kTI];
-#pragma unroll
-        for (int r = 0; r < kTI; r++) mm[r] = 0x7fffffff;
-        bool wild_hit = wild;   // a tetrad too spread out for the bias: flag every pair it is in
+        // Evaluate the masked blocks; after each partner group g the per-lane results are folded into
+        // ONE warp-wide 8-bit OR (redux.sync): bit r = some atom of my group r lies within the cutoff of
+        // some atom of partner group g.  The refined mask goes to the force pass, which then touches
+        // only those 32 x 32 blocks.
+        unsigned long long refined = 0ull;
 #pragma unroll 1
         for (int g = 0; g < 8; g++) {
             const unsigned m8 = (unsigned)(m >> (8 * g)) & 0xffu;
             if (!m8) continue;
+            int mm[kTI];
+#pragma unroll
+            for (int r = 0; r < kTI; r++) mm[r] = 0x7fffffff;
             const int jhi = 32 * g + 32;
 #pragma unroll 2
             for (int j = 32 * g; j < jhi; j += 2) {
@@ -480,11 +486,14 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
                     }
                 }
             }
-        }
-        bool pred = wild_hit;
+            unsigned mine8 = 0;
 #pragma unroll
-        for (int r = 0; r < kTI; r++) pred = pred || (mm[r] <= hthr[r]);
-        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);
+            for (int r = 0; r < kTI; r++) mine8 |= (mm[r] <= hthr[r]) ? (1u << r) : 0u;
+            refined |= (unsigned long long)__reduce_or_sync(0xffffffffu, mine8) << (8 * g);
+        }
+        // a tetrad too spread out for the bias: keep every block the sphere tests let through
+        if (__any_sync(0xffffffffu, wild)) refined = m;
+        if (refined) publish_hit(A, k, lane, refined);
         pr = pr_next;
         k = kn;
         it++;
@@ -492,13 +501,13 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
     }   // blocks of the work list
 }
 
-cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
+cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* work, const int* param_id, const int* perm, const unsigned char* need,
-                                unsigned char* const* peers, int world, cudaStream_t st) {
+                                unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
-        cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
+        cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
     // work buffer: [0] the item counter (16-byte slot), then one CullItem per listed pair at most
@@ -627,17 +636,17 @@ __global__ void __launch_bounds__(kScanThreads, 16) nb_scan32_kernel(ScanArgs A)
         bool pred = wild;
 #pragma unroll
         for (int r = 0; r < kTI; r++) pred = pred || (mm[r] <= hthr[r]);
-        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane);
+        if (__any_sync(0xffffffffu, pred)) publish_hit(A, k, lane, ~0ull);
         pr = pr_next;
     }
 }
 
-cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned char* hit,
+cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                            long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
-                           unsigned char* const* peers, int world, cudaStream_t st) {
+                           unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {   // (peer mode: the buffers are zeroed by the double-buffer protocol in engine.cu)
-        cudaError_t err = cudaMemsetAsync(hit + p0, 0, (size_t)(p1 - p0), st);
+        cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
     const long long want = p1 - p0;
@@ -657,176 +666,221 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 }
 
 // ---------------------------------------------------------------------------------------------
+// Exact force pass (edmd.cpp:258-276, worker.cpp:166-179, master.cpp:297-322).
+//
+// One CTA per tetrad that takes part in a flagged pair; warp w owns slot group w of the tetrad (the
+// spatially compact group of <= 32 atoms the scan's block masks refer to), lane l the atom in slot
+// 32w + l.  The eight warps walk the tetrad's partners independently (no CTA barrier inside the walk):
+//   * 32 adjacency entries at a time, each lane fetches one entry's block mask and reduces it to the
+//     8-bit set of PARTNER groups that can reach this warp's group; entries with an empty set are
+//     skipped by a ballot — for the typical contact only one or two warps of the CTA have work;
+//   * for a kept partner the warp gathers the atoms of those partner groups in ASCENDING ATOM ORDER
+//     (per-set table atom -> group) into its own shared-memory strip, then every lane runs the
+//     reference's expression tree against each gathered atom.
+// Bit-exactness: a lane adds its atom's contributions in ascending partner-atom order starting from
+// +0.0 per pair, then adds the pair partial to the tetrad total in pair-list order — the reference's
+// order.  Skipped atom pairs lie outside the effective cutoff and would add +-0.0, which never
+// changes a sum that started at +0.0.  d = x(t1) - x(t2) and the sign of the update depend on which
+// end of the pair this tetrad is, but  F1_i -= d * pf  and  F2_j += d * pf  are both, exactly,
+// "mine += (x_partner - x_mine) * pf" (negation commutes with IEEE rounding), so one form serves.
+constexpr int kAccBuf = 128;    // gathered partner atoms per round (4 chunks of 32)
+
 struct AccArgs {
     const double* crd;         // [n][3][S]
     const int* natoms;         // [n]
     const int* param_id;       // [n]
     const double* chg;         // [P][S] charges (abq[3i+2])
-    const unsigned char* hit;  // [np]
+    const unsigned long long* hit;   // [np] block masks from the distance pass; 0 = pair not flagged
     const long long* adj_off;  // [n+1] CSR over tetrads
     const int* adj_partner;    // partner index; bit 31 set when THIS tetrad is t2 of the pair
-    const int* adj_pair;       // pair index (for the hit flag)
+    const int* adj_pair;       // pair index (for the mask)
+    const int* perm;           // [P][kMaxStride] slot -> atom (-1 = empty slot)
+    const unsigned long long* grp;   // [P][32]: byte c of entry l = slot group of atom 32c + l (0xff = no atom)
     double* fnb;               // [n][3][S] out, clipped
     double* e_nb;              // [n][2] out: NB energy, electrostatic energy (unclipped)
     int t0;
     int S;
-    double cut2;               // atom_Cutoff^2
     double cut2_eff;           // see file header
     double krep, qfac;
-    int use_hits;              // 0: treat every pair as flagged
     int clip;                  // 1: clamp force components to [-1,1] (master.cpp:304-305)
 };
 
 struct AccSmem {
-    double sx[kMaxStride], sy[kMaxStride], sz[kMaxStride], sq[kMaxStride];
-    unsigned sFlag[kWarps];
+    double px[kWarps][kAccBuf], py[kWarps][kAccBuf], pz[kWarps][kAccBuf], pq[kWarps][kAccBuf];
+    double f[3][kMaxStride];   // clipped force by ATOM index (hand-over to the integrate half)
     double red[2][kWarps];
 };
 
-// Accumulates, clips and stores the NB force of tetrad t; leaves this thread's clipped force in f[].
-__device__ __forceinline__ void nb_accumulate_tetrad(const AccArgs& A, int t, AccSmem& sm, double f[3]) {
-    double* sx = sm.sx; double* sy = sm.sy; double* sz = sm.sz; double* sq = sm.sq;
-    unsigned* sFlag = sm.sFlag;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// bits g of the result = bits 8g + r of m, g = 0..7 (one multiply gathers the eight strided bits:
+// bit 8g' times 2^(56-7g) lands on bit 56+g only for g' = g, and no two products collide)
+__device__ __forceinline__ unsigned column_bits(unsigned long long m, int r) {
+    return (unsigned)((((m >> r) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+
+template <bool HAS_Q>
+__device__ __forceinline__ void acc_partner(const AccArgs& A, AccSmem& sm, int w, int lane, int u, unsigned pm,
+                                            double xi, double yi, double zi, double qi,
+                                            double& F0, double& F1, double& F2, double& E0, double& E1) {
+    const unsigned full = 0xffffffffu;
     const int S = A.S;
-    const int na = A.natoms[t];
-    const bool on = tid < na;
-    const double* X = A.crd + (size_t)t * 3 * S;
-    double xi = 0, yi = 0, zi = 0, qi = 0;
-    if (on) {
-        xi = X[tid]; yi = X[S + tid]; zi = X[2 * S + tid];
-        qi = A.chg[(size_t)A.param_id[t] * S + tid];
+    const int psu = A.param_id[u];
+    const double* U = A.crd + (size_t)u * 3 * S;
+    const unsigned long long gw = A.grp[(size_t)psu * 32 + lane];
+    const double k14 = __dmul_rn(0.25, A.krep), km2 = __dmul_rn(-2.0, A.krep);
+    const double q12 = __dmul_rn(0.5, A.qfac), q2 = __dmul_rn(2.0, A.qfac);
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;   // per-pair partial, starts at 0 (edmd.cpp:245-246)
+    double pe0 = 0.0, pe1 = 0.0;
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+        int cnt = 0;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+            const int c = 4 * half + c4;
+            const unsigned gj = (unsigned)(gw >> (8 * c)) & 0xffu;
+            const bool want = gj < 8u && ((pm >> gj) & 1u);
+            const unsigned bits = __ballot_sync(full, want);
+            if (want) {
+                const int j = 32 * c + lane;
+                const int pos = cnt + __popc(bits & ((1u << lane) - 1u));
+                sm.px[w][pos] = U[j]; sm.py[w][pos] = U[S + j]; sm.pz[w][pos] = U[2 * S + j];
+                if (HAS_Q) sm.pq[w][pos] = A.chg[(size_t)psu * S + j];
+            }
+            cnt += __popc(bits);
+        }
+        __syncwarp();
+#pragma unroll 2
+        for (int jj = 0; jj < cnt; jj++) {
+            const double dx = __dsub_rn(sm.px[w][jj], xi), dy = __dsub_rn(sm.py[w][jj], yi), dz = __dsub_rn(sm.pz[w][jj], zi);
+            double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));   // edmd.cpp:256
+            if (r2 < 1e-9) r2 = 1e-9;
+            if (r2 < A.cut2_eff) {
+                const double d = __dsub_rn(2.0, r2);
+                const double a = 0.0 < d ? d : 0.0;                                         // :260
+                pe0 = __dadd_rn(pe0, __dmul_rn(__dmul_rn(k14, a), a));                       // :264
+                double pf = __dmul_rn(km2, a);                                               // :268
+                if (HAS_Q) {
+                    const double qq = __dmul_rn(qi, sm.pq[w][jj]);                           // :261 (a product commutes)
+                    pe1 = __dadd_rn(pe1, __dmul_rn(__dmul_rn(q12, qq), r2));                 // :265
+                    pf = __dsub_rn(pf, __ddiv_rn(__dmul_rn(q2, qq), __dmul_rn(r2, r2)));
+                }
+                g0 = __dadd_rn(g0, __dmul_rn(dx, pf));                                       // :269-275
+                g1 = __dadd_rn(g1, __dmul_rn(dy, pf));
+                g2 = __dadd_rn(g2, __dmul_rn(dz, pf));
+            }
+        }
+        __syncwarp();
     }
-    double F0 = 0.0, F1 = 0.0, F2 = 0.0;   // tetrad totals, pair-list order (worker.cpp:173-178)
-    double E0 = 0.0, E1 = 0.0;             // this thread's share of the pair energies
+    F0 = __dadd_rn(F0, g0); F1 = __dadd_rn(F1, g1); F2 = __dadd_rn(F2, g2);   // worker.cpp:173-178
+    E0 += pe0; E1 += pe1;
+}
+
+// Accumulates, clips and stores the NB force of tetrad t; leaves the clipped force of ATOM threadIdx.x
+// in f[] (the integrate half maps thread <-> atom).
+template <bool HAS_Q>
+__device__ __forceinline__ void nb_accumulate_tetrad(const AccArgs& A, int t, AccSmem& sm, double f[3]) {
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int S = A.S;
+    const int ps = A.param_id[t];
+    const int na = A.natoms[t];
+    const int a = A.perm[(size_t)ps * kMaxStride + tid];     // my atom (slot order: warp w = group w)
+    const bool on = a >= 0;
+    const double* X = A.crd + (size_t)t * 3 * S;
+    // an empty slot sits far away from everything: it never passes the cutoff test
+    double xi = 1e150, yi = 1e150, zi = 1e150, qi = 0.0;
+    if (on) {
+        xi = X[a]; yi = X[S + a]; zi = X[2 * S + a];
+        if (HAS_Q) qi = A.chg[(size_t)ps * S + a];
+    }
+    double F0 = 0.0, F1 = 0.0, F2 = 0.0;   // tetrad totals, pair-list order
+    double E0 = 0.0, E1 = 0.0;             // this lane's share of the pair energies
 
     const long long e_begin = A.adj_off[t], e_end = A.adj_off[t + 1];
-    for (long long base = e_begin; base < e_end; base += kThreads) {
-        // 256 partners at a time: who is flagged?
-        const long long e = base + tid;
-        bool flagged = false;
-        if (e < e_end) flagged = A.use_hits ? (A.hit[A.adj_pair[e]] != 0) : true;
-        const unsigned bal = __ballot_sync(0xffffffffu, flagged);
-        if (lane == 0) sFlag[warp] = bal;
-        __syncthreads();
-        unsigned flags[kWarps];
-#pragma unroll
-        for (int w = 0; w < kWarps; w++) flags[w] = sFlag[w];
-        __syncthreads();
-#pragma unroll 1
-        for (int w = 0; w < kWarps; w++) {
-            unsigned f = flags[w];
-            while (f) {
-                const int b = __ffs(f) - 1;
-                f &= f - 1;
-                const long long ee = base + w * 32 + b;
-                const int code = A.adj_partner[ee];
+    for (long long base = e_begin; base < e_end; base += 32) {
+        const long long e = base + lane;
+        unsigned pmv = 0; int code = 0;
+        if (e < e_end) {
+            const unsigned long long m = A.hit[A.adj_pair[e]];
+            if (m) {
+                code = A.adj_partner[e];
                 const int u = code & 0x7fffffff;
-                const bool me_second = code < 0;   // this tetrad is t2 of the reference pair
-                const int nu = A.natoms[u];
-                const double* U = A.crd + (size_t)u * 3 * S;
-                if (tid < nu) {
-                    sx[tid] = U[tid]; sy[tid] = U[S + tid]; sz[tid] = U[2 * S + tid];
-                    sq[tid] = A.chg[(size_t)A.param_id[u] * S + tid];
-                }
-                __syncthreads();
-                if (on) {
-                    double g0 = 0.0, g1 = 0.0, g2 = 0.0;   // per-pair partial, starts at 0 (edmd.cpp:245-246)
-                    double pe0 = 0.0, pe1 = 0.0;
-                    for (int j = 0; j < nu; j++) {
-                        // d = x(t1) - x(t2), edmd.cpp:251-253
-                        double dx, dy, dz;
-                        if (me_second) { dx = __dsub_rn(sx[j], xi); dy = __dsub_rn(sy[j], yi); dz = __dsub_rn(sz[j], zi); }
-                        else           { dx = __dsub_rn(xi, sx[j]); dy = __dsub_rn(yi, sy[j]); dz = __dsub_rn(zi, sz[j]); }
-                        double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                        if (r2 < 1e-9) r2 = 1e-9;
-                        if (r2 < A.cut2_eff) {
-                            const double a = __dsub_rn(2.0, r2) > 0.0 ? __dsub_rn(2.0, r2) : 0.0;
-                            const double qq = __dmul_rn(me_second ? sq[j] : qi, me_second ? qi : sq[j]);
-                            pe0 = __dadd_rn(pe0, __dmul_rn(__dmul_rn(__dmul_rn(0.25, A.krep), a), a));
-                            pe1 = __dadd_rn(pe1, __dmul_rn(__dmul_rn(__dmul_rn(0.5, A.qfac), qq), r2));
-                            const double pf = __dsub_rn(__dmul_rn(__dmul_rn(-2.0, A.krep), a),
-                                                        __ddiv_rn(__dmul_rn(__dmul_rn(2.0, A.qfac), qq), __dmul_rn(r2, r2)));
-                            if (me_second) {   // F2_j += d * pf, edmd.cpp:273-275
-                                g0 = __dadd_rn(g0, __dmul_rn(dx, pf)); g1 = __dadd_rn(g1, __dmul_rn(dy, pf)); g2 = __dadd_rn(g2, __dmul_rn(dz, pf));
-                            } else {           // F1_i -= d * pf, edmd.cpp:269-271
-                                g0 = __dsub_rn(g0, __dmul_rn(dx, pf)); g1 = __dsub_rn(g1, __dmul_rn(dy, pf)); g2 = __dsub_rn(g2, __dmul_rn(dz, pf));
-                            }
-                        }
-                    }
-                    F0 = __dadd_rn(F0, g0); F1 = __dadd_rn(F1, g1); F2 = __dadd_rn(F2, g2);
-                    E0 += pe0; E1 += pe1;
-                }
-                __syncthreads();
+                // mask bit 8g + r: group r of the lower-numbered tetrad x group g of the higher-numbered one
+                pmv = t < u ? column_bits(m, w) : (unsigned)(m >> (8 * w)) & 0xffu;
             }
+        }
+        unsigned todo = __ballot_sync(full, pmv != 0u);
+        while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int u = __shfl_sync(full, code, b) & 0x7fffffff;
+            const unsigned pm = __shfl_sync(full, pmv, b);
+            acc_partner<HAS_Q>(A, sm, w, lane, u, pm, xi, yi, zi, qi, F0, F1, F2, E0, E1);
         }
     }
 
-    // clip (master.cpp:304-305) and store; energies are sums over this tetrad's atoms
-    double* F = A.fnb + (size_t)t * 3 * S;
-    f[0] = F0; f[1] = F1; f[2] = F2;
+    // clip (master.cpp:304-305) and store
+    double c0 = F0, c1 = F1, c2 = F2;
     if (A.clip) {
-        f[0] = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
-        f[1] = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
-        f[2] = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
+        c0 = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
+        c1 = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
+        c2 = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
     }
+    double* F = A.fnb + (size_t)t * 3 * S;
     if (on) {
-        F[tid] = f[0]; F[S + tid] = f[1]; F[2 * S + tid] = f[2];
-    } else if (tid < S) {
-        F[tid] = 0.0; F[S + tid] = 0.0; F[2 * S + tid] = 0.0;
+        F[a] = c0; F[S + a] = c1; F[2 * S + a] = c2;
+        sm.f[0][a] = c0; sm.f[1][a] = c1; sm.f[2][a] = c2;
     }
     double ev[2] = {E0, E1};
-    block_sum<2>(ev, sm.red);
+    block_sum<2>(ev, sm.red);              // (also the barrier that publishes sm.f)
     if (tid == 0) { A.e_nb[2 * (size_t)t] = ev[0]; A.e_nb[2 * (size_t)t + 1] = ev[1]; }
+    f[0] = f[1] = f[2] = 0.0;
+    if (tid < na) { f[0] = sm.f[0][tid]; f[1] = sm.f[1][tid]; f[2] = sm.f[2][tid]; }
+    __syncthreads();                       // sm.f is rewritten by this CTA's next tetrad
 }
 
+template <bool HAS_Q>
 __global__ void __launch_bounds__(kThreads, 2) nb_accumulate_kernel(AccArgs A) {
     __shared__ AccSmem sm;
     double f[3];
-    nb_accumulate_tetrad(A, A.t0 + blockIdx.x, sm, f);
-}
-
-// Fused tail of the step: NB accumulate + clip (master.cpp:297-322), then update_Velocities and
-// update_Coordinates (edmd.cpp:289-327) with the clipped force still in registers — the N x 3S
-// force array is written once for the caller (edmd_get_forces) but never read back.
-// Other CTAs read this tetrad's coordinates as a partner while it is being integrated, so the new
-// coordinates go to a SECOND buffer (I.crd_out); the next ED pass reads them from there.
-__global__ void __launch_bounds__(kThreads, 4) nb_finish_kernel(AccArgs A, IntArgs I) {
-    __shared__ AccSmem sm;
-    __shared__ double red[1][kWarps];
-    const int t = A.t0 + blockIdx.x;
-    double f[3];
-    nb_accumulate_tetrad(A, t, sm, f);
-    // (loading the integrate operands before the flag scan was tried: the extra live registers
-    // spill and the kernel gets slower — 1.41 vs 1.27 ms at 1e5 tetrads)
-    integrate_tetrad(I, t, f, red);
+    nb_accumulate_tetrad<HAS_Q>(A, A.t0 + blockIdx.x, sm, f);
 }
 
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
-                                 const unsigned char* hit, const long long* adj_off, const int* adj_partner,
-                                 const int* adj_pair, double* fnb, double* e_nb, int t0, int count, int S,
-                                 const SimParams& sp, int use_hits, int clip, cudaStream_t st) {
+                                 const unsigned long long* hit, const long long* adj_off, const int* adj_partner,
+                                 const int* adj_pair, const int* perm, const unsigned long long* grp, double* fnb,
+                                 double* e_nb, int t0, int count, int S, const SimParams& sp, int clip, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
-    AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
-              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, use_hits, clip};
-    nb_accumulate_kernel<<<count, kThreads, 0, st>>>(A);
+    AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, e_nb, t0, S,
+              nb_effective_cut2(sp), sp.krep, sp.qfac, clip};
+    if (sp.qfac != 0.0) nb_accumulate_kernel<true><<<count, kThreads, 0, st>>>(A);
+    else                nb_accumulate_kernel<false><<<count, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }
 
-// ---- per-tetrad hit marks ------------------------------------------------------------------------
-// tet_mark[t] = 1 iff tetrad t takes part in at least one flagged pair.  Almost every tetrad has none,
-// and then the tail of the step is a pure streaming update: the fused kernel is split into a lean
-// kernel for unmarked tetrads (few registers, 6 CTAs/SM, no adjacency walk) and the full kernel for
-// marked ones; both are launched over all owned tetrads and return at once for the other's share.
-__global__ void mark_tetrads_kernel(const unsigned char* hit, const int2* pairs, long long np, unsigned char* mark) {
+// ---- the fused tail of the step ---------------------------------------------------------------------
+// NB accumulate + clip (master.cpp:297-322), then update_Velocities and update_Coordinates
+// (edmd.cpp:289-327) with the clipped force still on chip.  Other CTAs read a tetrad's coordinates as
+// a partner while it is being integrated, so the new coordinates go to a SECOND buffer (I.crd_out); the
+// next ED pass reads them from there.
+//
+// Almost every tetrad has no flagged pair, and then the tail is a pure streaming update.
+//   mark_tetrads_kernel     flagged pair -> both ends marked; the first marker of an owned tetrad appends
+//                           it to a compact list (the order of the list varies from run to run, each
+//                           tetrad's result does not depend on it);
+//   finish_unmarked_kernel  lean integrate for unmarked tetrads (few registers, no adjacency walk);
+//   finish_marked_kernel    a grid sized for the SMs walks the compact list, one CTA per marked tetrad.
+__global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* pairs, long long np, int* mark,
+                                    int* list, unsigned* count, int t0, int t1) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
-        if (hit[p]) { const int2 pr = pairs[p]; mark[pr.x] = 1; mark[pr.y] = 1; }
+        if (!hit[p]) continue;
+        const int2 pr = pairs[p];
+        if (pr.x >= t0 && pr.x < t1 && atomicExch(&mark[pr.x], 1) == 0) list[atomicAdd(count, 1u)] = pr.x;
+        if (pr.y >= t0 && pr.y < t1 && atomicExch(&mark[pr.y], 1) == 0) list[atomicAdd(count, 1u)] = pr.y;
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const unsigned char* mark,
+__global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const int* mark,
                                                                     unsigned char* dirty, double* fnb, double* e_nb) {
     __shared__ double red[1][kWarps];
     const int t = I.t0 + blockIdx.x;
@@ -840,72 +894,49 @@ __global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I,
     integrate_tetrad(I, t, zero, red);
 }
 
-// Persistent: a few CTAs sweep the mark bytes 256 at a time (marked tetrads are rare, an early-exit
-// CTA per tetrad would cost more than the sweep) and process the marked ones.
-__global__ void __launch_bounds__(kThreads, 2) finish_marked_kernel(AccArgs A, IntArgs I, const unsigned char* mark,
-                                                                  unsigned char* dirty, int count) {
+template <bool HAS_Q>
+__global__ void __launch_bounds__(kThreads, 2) finish_marked_kernel(AccArgs A, IntArgs I, const int* list,
+                                                                  const unsigned* count, unsigned char* dirty) {
     __shared__ AccSmem sm;
     __shared__ double red[1][kWarps];
-    __shared__ unsigned sMarks;
-    const int tid = threadIdx.x;
-    for (int base = blockIdx.x * 32; base < count; base += gridDim.x * 32) {   // 32-tetrad windows
-        if (tid < 32) {
-            const int e = base + tid;
-            const unsigned bal = __ballot_sync(0xffffffffu, e < count && mark[A.t0 + e] != 0);
-            if (tid == 0) sMarks = bal;
-        }
-        __syncthreads();
-        unsigned f = sMarks;
-        __syncthreads();
-        while (f) {
-            const int b = __ffs(f) - 1;
-            f &= f - 1;
-            const int t = A.t0 + base + b;
-            double fr[3];
-            nb_accumulate_tetrad(A, t, sm, fr);
-            if (tid == 0) dirty[t] = 1;
-            integrate_tetrad(I, t, fr, red);
-            __syncthreads();
-        }
+    const unsigned total = *count;
+    for (unsigned i = blockIdx.x; i < total; i += gridDim.x) {
+        const int t = list[i];
+        double fr[3];
+        nb_accumulate_tetrad<HAS_Q>(A, t, sm, fr);
+        if (threadIdx.x == 0) dirty[t] = 1;
+        integrate_tetrad(I, t, fr, red);
     }
 }
 
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
-                                   const unsigned char* hit, const int2* pairs, long long np, const long long* adj_off,
-                                   const int* adj_partner, const int* adj_pair, double* fnb, double* e_nb,
+                                   const unsigned long long* hit, const int2* pairs, long long np, const long long* adj_off,
+                                   const int* adj_partner, const int* adj_pair, const int* perm,
+                                   const unsigned long long* grp, double* fnb, double* e_nb,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
-                                   const double* rnd, double* temp, unsigned char* mark, unsigned char* dirty, int n,
-                                   int t0, int count, int S, const SimParams& sp, cudaStream_t st) {
+                                   const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
+                                   int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(mark, 0, (size_t)n, st);
+    // mark[0..n) flags, then the list counter, then the compact list of marked owned tetrads
+    unsigned* cnt = reinterpret_cast<unsigned*>(mark + n);
+    int* list = mark + n + 1;
+    cudaError_t err = cudaMemsetAsync(mark, 0, sizeof(int) * ((size_t)n + 1), st);
     if (err != cudaSuccess) return err;
     if (np > 0) {
         long long blocks = (np + 255) / 256;
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        mark_tetrads_kernel<<<(int)blocks, 256, 0, st>>>(hit, pairs, np, mark);
+        if (blocks > sms * 16) blocks = sms * 16;
+        mark_tetrads_kernel<<<(int)blocks, 256, 0, st>>>(hit, pairs, np, mark, list, cnt, t0, t0 + count);
     }
-    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
-    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
-              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1, 1};
+    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, e_nb, t0, S,
+              nb_effective_cut2(sp), sp.krep, sp.qfac, 1};
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
     finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
-    int sweep = (count + 31) / 32;
-    if (sweep > 148 * 2) sweep = 148 * 2;
-    finish_marked_kernel<<<sweep, kThreads, 0, st>>>(A, I, mark, dirty, count);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_nb_finish(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
-                             const unsigned char* hit, const long long* adj_off, const int* adj_partner,
-                             const int* adj_pair, double* fnb, double* e_nb, const ParamSets& ps, double* vel,
-                             double* crd_out, const double* fed, const double* rnd, double* temp, int t0, int count,
-                             int S, const SimParams& sp, cudaStream_t st) {
-    if (count <= 0) return cudaSuccess;
-    const double cut2 = sp.atom_cutoff * sp.atom_cutoff;
-    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, fnb, e_nb, t0, S,
-              cut2, nb_effective_cut2(sp), sp.krep, sp.qfac, 1, 1};
-    IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
-    nb_finish_kernel<<<count, kThreads, 0, st>>>(A, I);
+    if (np > 0) {
+        // the number of marked tetrads is only known on the device: a grid that fills the SMs walks the list
+        const int grid = count < 4 * sms ? count : 4 * sms;
+        if (sp.qfac != 0.0) finish_marked_kernel<true><<<grid, kThreads, 0, st>>>(A, I, list, cnt, dirty);
+        else                finish_marked_kernel<false><<<grid, kThreads, 0, st>>>(A, I, list, cnt, dirty);
+    }
     return cudaGetLastError();
 }
 

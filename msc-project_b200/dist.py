@@ -143,7 +143,8 @@ class EngineBackend:
     def hit_tensor(self):
         ptr, nbytes = self.e.device_buffer(self.e.BUF_HIT)
         if self._hit is None or self._hit[0] != (ptr, nbytes):
-            self._hit = ((ptr, nbytes), self._wrap(self.e.BUF_HIT, "|u1", 1, self.torch.uint8))
+            # one 64-bit block mask per pair (0 = not flagged), see nb.cu
+            self._hit = ((ptr, nbytes), self._wrap(self.e.BUF_HIT, "<i8", 8, self.torch.int64))
         return self._hit[1]
 
     def invalidate(self):

@@ -119,6 +119,7 @@ def load_library():
         "edmd_timing_reset": (C.c_int, [E]),
         "edmd_launch_count": (LL, [E]),
         "edmd_nb_stats": (C.c_int, [E, C.POINTER(LL)]),
+        "edmd_nb_stats_ex": (C.c_int, [E, C.POINTER(LL)]),
         "edmd_alloc_pinned": (C.c_void_p, [C.c_size_t]),
         "edmd_free_pinned": (None, [C.c_void_p]),
         "edmd_measure_fp64_peak": (C.c_int, [C.c_int, PD, PD]),
@@ -454,6 +455,17 @@ class Engine:
         c = C.c_longlong()
         self._ck(self.lib.edmd_nb_stats(self.h, C.byref(c)))
         return c.value
+
+
+def _nb_stats(self) -> dict:
+    """Counts from the last NB pass: flagged tetrad pairs, marked (owned) tetrads, 32 x 32 atom blocks the
+    force pass evaluates, tetrad pairs selected by the bounding-sphere tests."""
+    out = (C.c_longlong * 4)()
+    self._ck(self.lib.edmd_nb_stats_ex(self.h, out))
+    return dict(flagged_pairs=out[0], marked_tetrads=out[1], force_blocks=out[2], selected_pairs=out[3])
+
+
+Engine.nb_stats = _nb_stats
 
 
 def measure_fp64_peak(device=0):

@@ -199,16 +199,20 @@ def make_ring(n_tetrads: int, kind: str = "ring", nev: int = 12, seed: int = GEN
                       params, f"{kind}{n}")
 
 
-def make_ragged(n_tetrads: int = 40, seed: int = GENERATOR_SEED, nevs=(3, 12, 20, 29), lap_gap: float = 9.0) -> EdmdSystem:
+def make_ragged(n_tetrads: int = 40, seed: int = GENERATOR_SEED, nevs=(3, 12, 20, 29), lap_gap: float = 9.0,
+                bp_lo: int = 58, bp_hi: int = 64, full_tetrad: bool = True) -> EdmdSystem:
     """Edge-case system: base pairs with DIFFERENT atom counts (58..64, one 64-atom base pair so a
     tetrad can reach the 256-atom limit), every tetrad with its own parameter set, and eigenvector
     counts below, at and above the 12-per-chunk register tile of the ED kernel.  Geometry: the
-    double coil of make_ring (real atom overlaps)."""
+    double coil of make_ring (real atom overlaps).  ``bp_lo/bp_hi`` (exclusive) bound the atoms kept per
+    base pair; ``full_tetrad=False`` leaves out the 256-atom tetrad, so small base pairs give a system
+    whose atom stride is below the engine maximum."""
     base = make_ring(n_tetrads, kind="coil", laps=2, lap_gap=lap_gap)
     rng = np.random.default_rng(seed + 1)
     n = n_tetrads
-    bp_atoms = rng.integers(58, 64, size=n + 3).astype(np.int32)
-    bp_atoms[5:9] = 64                      # tetrad 5 = 4 x 64 = 256 atoms (engine maximum)
+    bp_atoms = rng.integers(bp_lo, bp_hi, size=n + 3).astype(np.int32)
+    if full_tetrad:
+        bp_atoms[5:9] = 64                  # tetrad 5 = 4 x 64 = 256 atoms (engine maximum)
     bp_atoms[n:n + 3] = bp_atoms[0:3]       # the ring repeats its first three base pairs
     crd_bp = base.crd.reshape(n, 4, 63, 3)
     extra = rng.normal(scale=0.5, size=(n + 3, 1, 3))   # 64th atom: near atom 0 of the base pair

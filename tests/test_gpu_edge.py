@@ -224,3 +224,130 @@ def test_both_projection_kernels_match_the_oracle(edmd, po):
             assert rel(cg, co) < TOL
             out.append((fg["ed"], cg))
         assert rel(out[0][0], out[1][0]) < 1e-12 and rel(out[0][1], out[1][1]) < 1e-13
+
+
+def test_small_atom_stride_system(edmd, po):
+    """Every tetrad has at most 224 atoms, so the atom stride S is below the engine maximum of 256 while the
+    culling groups still address 8 x 32 slots: the slot tables must not depend on S (a round-1 overflow)."""
+    s = edmd.make_ragged(40, bp_lo=50, bp_hi=57, full_tetrad=False)
+    assert s.num_atoms.max() <= 224
+    o = po.Oracle(s, "port"); g = edmd.Engine(s)
+    assert g.atom_stride < 256
+    assert g.build_pairlist() == o.build_pairs()
+    o.forces(random_on=False); g.ed_forces(); g.nb_forces()
+    fo, fg = o.get_forces(), g.get_forces()
+    assert np.count_nonzero(fo["nb"]) > 50
+    assert rel(fg["ed"], fo["ed"]) < TOL and rel(fg["nb"], fo["nb"]) < TOL and rel(fg["nb_energy"], fo["nb_energy"]) < TOL
+    out = []
+    for mode in (0, 1, 2, 4):
+        h = edmd.Engine(s); h.set_nb_scan_mode(mode); h.build_pairlist(); h.set_rng(9, 1, 0); h.step(4, random_mode=1)
+        out.append(h.get_state())
+    o2 = po.Oracle(s, "port"); o2.set_time(9); o2.set_rng_calls(0); o2.build_pairs(); o2.step(4, random_on=True)
+    co, vo = o2.get_state()
+    for c, v in out:
+        assert np.array_equal(c, out[0][0]) and np.array_equal(v, out[0][1])
+    assert rel(out[0][0], co) < TOL and rel(out[0][1], vo) < TOL
+
+
+@pytest.mark.parametrize("qfac", [0.0, 332.064 / 4.0])
+def test_block_masked_force_pass_equals_all_blocks(edmd, po, qfac):
+    """The culled distance pass hands the force pass a refined 8 x 8 block mask per pair; the brute-force
+    passes hand it all ones.  Forces, energies and trajectories must be bit-identical either way, with and
+    without electrostatics (every atom pair inside atom_Cutoff counts when qfac != 0)."""
+    s = edmd.make_ring(120, kind="coil", laps=3, lap_gap=9.0)
+    res = []
+    for mode in (0, 4):
+        g = edmd.Engine(s); g.set_nb_consts(100.0, qfac); g.set_nb_scan_mode(mode); g.build_pairlist()
+        g.ed_forces(); g.nb_forces()
+        f = g.get_forces()
+        g.step(3)
+        res.append((f["nb"], f["nb_energy"], g.get_state(), g.flagged_pairs()))
+    assert np.count_nonzero(res[0][0]) > 100
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2][0], res[1][2][0]) and np.array_equal(res[0][2][1], res[1][2][1])
+    assert res[1][3] >= res[0][3] >= 1
+    o = po.Oracle(s, "port"); o.set_nb_consts(100.0, qfac); o.build_pairs(); o.forces(random_on=False)
+    assert rel(res[1][0], o.get_forces()["nb"]) < TOL
+
+
+def _adjoint_column_norms(ref, mov):
+    """Squared norms of the four quaternion candidates in the order FastCalcRMSDAndRotation tries them
+    (qcprot.c:252-309): columns 1, 2, 4, 3 of adj(K - lambda_max I)."""
+    a = ref - ref.mean(axis=0); x = mov - mov.mean(axis=0)
+    m = a.T @ x
+    (xx, xy, xz), (yx, yy, yz), (zx, zy, zz) = m
+    k = np.array([[xx + yy + zz, yz - zy, zx - xz, xy - yx],
+                  [yz - zy, xx - yy - zz, xy + yx, zx + xz],
+                  [zx - xz, xy + yx, -xx + yy - zz, yz + zy],
+                  [xy - yx, zx + xz, yz + zy, -xx - yy + zz]])
+    lam = np.linalg.eigvalsh(k).max()
+    b = k - lam * np.eye(4)
+    adj = np.empty((4, 4))
+    for i in range(4):
+        for j in range(4):
+            adj[j, i] = (-1) ** (i + j) * np.linalg.det(np.delete(np.delete(b, i, 0), j, 1))
+    return [float(adj[:, c] @ adj[:, c]) for c in (0, 1, 3, 2)]
+
+
+def test_qcp_fallback_branches(edmd, po):
+    """Force every exit of the quaternion fallback chain (qcprot.c:252-309): a structure that is EXACTLY its
+    average turned by 180 degrees about x / z / y makes the first one / two / three adjoint columns vanish,
+    and a structure collapsed to a point makes all four vanish (identity rotation).  The structures are
+    0.05 x DNA-sized so that a vanishing column is far below, and a good one far above, evecprec = 1e-6."""
+    base = edmd.make_gc90()
+    flips = [np.array([1.0, 1.0, 1.0]), np.array([1.0, -1.0, -1.0]), np.array([-1.0, -1.0, 1.0]),
+             np.array([-1.0, 1.0, -1.0]), None]
+    psets, crd = [], []
+    for k, d in enumerate(flips):
+        p = base.psets[k]
+        avg = (p.avg.reshape(-1, 3) - p.avg.reshape(-1, 3).mean(axis=0)) * 0.05
+        psets.append(edmd.ParamSet(p.num_atoms, p.num_evecs, np.ascontiguousarray(avg.reshape(-1)), p.masses3, p.abq,
+                                   p.evals, p.evecs))
+        x = avg * d if d is not None else np.tile(np.array([0.3, -0.2, 0.1]), (p.num_atoms, 1))
+        crd.append(x.reshape(-1))
+        norms = _adjoint_column_norms(avg, x)
+        want = {0: 0, 1: 1, 2: 2, 3: 3, 4: 4}[k]       # how many candidates must be rejected
+        assert all(v < 1e-12 for v in norms[:want]) and (want == 4 or norms[want] > 1e-3), (k, norms)
+    crd = np.concatenate(crd)
+    s = edmd.EdmdSystem(psets, np.arange(len(flips), dtype=np.int32), None, crd, np.zeros_like(crd))
+    o = po.Oracle(s, "port"); o.ed_forces()
+    g = edmd.Engine(s); g.ed_forces()
+    fo, fg = o.get_forces(), g.get_forces()
+    co, _ = o.get_state(); cg, _ = g.get_state()
+    assert np.all(np.isfinite(cg)) and np.all(np.isfinite(fg["ed"]))
+    assert np.abs(cg - co).max() < 1e-12 and np.abs(fg["ed"] - fo["ed"]).max() < 1e-12
+    assert np.abs(fg["ed_energy"] - fo["ed_energy"]).max() < 1e-12
+
+
+def test_c3_full_size_sampled_parity(edmd, po):
+    """BASELINE configs[3]: 100,000 tetrads, cutoff pair list (cell-list builder), Langevin random forces on.
+    The ring is clash-free, so every tetrad evolves independently of the others and sampled tetrads can be
+    checked against the oracle stepping those tetrads alone with the same random-stream call numbers
+    (call number = step * n + tetrad, edmd.cpp:173,179)."""
+    n = 100000
+    s = edmd.make_ring(n, kind="ring")
+    g = edmd.Engine(s)
+    npairs = g.build_pairlist()
+    assert 4 * n <= npairs <= 5 * n + 5
+    g.set_rng(424242, 1, 0)
+    steps = 3
+    g.step(steps, random_mode=1)
+    assert g.flagged_pairs() == 0
+    f = g.get_forces()
+    assert not np.any(f["nb"])
+    cg, vg = g.get_state()
+    pick = [0, 1, 31337, 50000, 99998, 99999]
+    sub = s.subset(pick)
+    o = po.Oracle(sub, "port"); o.set_time(424242)
+    for k in range(steps):
+        for i, t in enumerate(pick):
+            o.set_rng_calls(k * n + t)
+            o.ed_forces(i); o.random_terms(i, rank=1)
+            o.update_velocities(i); o.update_coordinates(i)
+    co, vo = o.get_state()
+    off = s.off3
+    idx = np.concatenate([np.arange(off[t], off[t + 1]) for t in pick])
+    assert np.array_equal(f["rnd"][idx], o.get_forces()["rnd"])
+    assert rel(cg[idx], co) < TOL and rel(vg[idx], vo) < TOL
+    g.merge(); c1, v1 = g.get_state(); g.merge(); c2, v2 = g.get_state()
+    assert rel(c2, c1) < 1e-15 and rel(v2, v1) < 1e-14
