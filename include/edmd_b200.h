@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EDMD_B200_ABI_VERSION 1
+#define EDMD_B200_ABI_VERSION 2
 
 typedef enum {
     EDMD_OK = 0,
@@ -138,17 +138,53 @@ int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long num_pairs);
  * Defaults: everything. */
 int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1);
 
-/* Fused distance pass + hit broadcast (multi-GPU, one process per GPU).  Instead of all-gathering the
- * per-pair hit bytes after the scan (what replaced the reference's MPI_Reduce, master.cpp:288), the
- * scan kernel stores every hit directly into the hit buffer of EVERY rank through peer pointers
- * over NVLink/NVSwitch (CUDA IPC); the only per-step collective left is a barrier between the scan
- * and the accumulate pass.  Protocol: after each pair-list (re)build every rank calls
- * edmd_peer_hits_export (two 64-byte IPC handles), the ranks exchange them, call
- * edmd_peer_hits_open with all world x 2 handles and then synchronise once.  The two buffers
- * alternate by step; each rank re-zeroes the one it has just consumed. */
-int edmd_peer_hits_export(edmd_engine* e, unsigned char* handles /* 128 bytes */);
-int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* world*128 bytes */, int world, int rank);
-int edmd_peer_hits_close(edmd_engine* e);
+/* ---- multi-GPU: one engine per GPU, exchanging through peer memory over NVLink/NVSwitch -------------
+ * Replaces the reference's per-step messages (master.cpp:268-292, worker.cpp:109-142; datatypes
+ * mpilib.cpp:23-130).  Every rank holds the whole system (as every MPI worker did, worker.cpp:67-87) and
+ * owns a contiguous block of ceil(n/world) tetrads plus a slice of the pair list (edmd_set_shard).  With
+ * peers attached, edmd_step runs the sharded step — ED and random terms for owned tetrads; flag barrier;
+ * pull of the non-owned tetrads this rank reads, straight from their owners' memory (MPI_Bcast(MPI_Crds),
+ * master.cpp:279); distance pass over the pair slice, whose kernel stores each flagged pair's block mask
+ * into EVERY rank's buffer (instead of the dense MPI_Reduce, master.cpp:288); flag barrier; force pass +
+ * clip + integrate for owned tetrads — all kernels on the engine stream, replayed as one CUDA graph.
+ * No force is ever reduced across ranks, so results are bit-identical for every world size.
+ *
+ * One process per GPU (torchrun): after the pair list exists every rank calls edmd_peer_export, the ranks
+ * exchange the blobs (any transport), call edmd_peer_attach with all of them in rank order, then
+ * edmd_set_shard.  When a later edmd_build_pairlist fails with EDMD_ERR_STATE because the list outgrew
+ * the mask buffer: edmd_peer_detach everywhere, export and attach again.  One process driving several
+ * GPUs: the edmd_group_* calls below do all of this internally. */
+#define EDMD_PEER_BLOB_BYTES 320
+int edmd_peer_export(edmd_engine* e, unsigned char* blob /* EDMD_PEER_BLOB_BYTES */);
+int edmd_peer_attach(edmd_engine* e, const unsigned char* blobs /* world * EDMD_PEER_BLOB_BYTES */, int world, int rank);
+int edmd_peer_detach(edmd_engine* e);
+/* Collective: make this rank's copy of every rank's owned data complete.  what = 1 coordinates | 2 velocities
+ * | 4 per-tetrad energies and temperatures.  Needed before edmd_merge, edmd_build_pairlist, edmd_get_state
+ * and edmd_get_energies; every rank must call it (it contains two barriers). */
+int edmd_peer_gather(edmd_engine* e, int what);
+int edmd_world(edmd_engine* e, int* world, int* rank);
+
+/* Single process, several GPUs (the C++ driver): a group owns one engine per device, keeps them in step
+ * and exposes the same operations as a single engine.  n_gpus engines on `devices` (NULL = 0..n_gpus-1).
+ * This is the `edmd_create(params, n_gpus, ...)` of a multi-GPU caller. */
+typedef struct edmd_group edmd_group;
+int  edmd_group_create(const edmd_params* p, int n_gpus, const int* devices, edmd_group** out);
+void edmd_group_destroy(edmd_group* g);
+int  edmd_group_size(edmd_group* g);
+edmd_engine* edmd_group_engine(edmd_group* g, int rank);   /* for the per-engine setters */
+int  edmd_group_upload_tetrads(edmd_group* g, const edmd_tetrad* tets, int n, const int* bp_atoms);
+int  edmd_group_set_state(edmd_group* g, const edmd_tetrad* tets, int n);
+int  edmd_group_get_state(edmd_group* g, edmd_tetrad* tets, int n);
+int  edmd_group_set_rng(edmd_group* g, long time0, int rank, long calls_before);
+/* edmd_build_pairlist on every GPU (the list is a pure function of the centroids) + the work split:
+ * contiguous tetrad blocks, equal pair slices (replaces Master::generate_Indexes, master.cpp:214-242). */
+int  edmd_group_build_pairlist(edmd_group* g, long long* num_pairs);
+int  edmd_group_step(edmd_group* g, int nsteps, int random_mode);
+int  edmd_group_merge(edmd_group* g);
+int  edmd_group_get_energies(edmd_group* g, double out[4]);
+int  edmd_group_snapshot_begin(edmd_group* g, int ticket, double* crd, double* vel, double* obs);
+int  edmd_group_snapshot_wait(edmd_group* g, int ticket);
+int  edmd_group_sync(edmd_group* g);
 
 /* ---- the five EDMD methods, batched over all (owned) tetrads ---------------------------- */
 /* EDMD::calculate_ED_Forces (edmd.cpp:64-166) incl. CalcRMSDRotationalMatrix
@@ -191,6 +227,15 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode);
  * the coordinate and velocity arrays are one slab each (edmd_alloc_pinned), the velocity upload
  * overlaps the ED and distance kernels.  Same results as the three separate calls. */
 int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int random_mode);
+/* Asynchronous output on a side stream (replaces the blocking gathers of Master::write_Info / write_Crds,
+ * master.cpp:388-419): the coordinates and velocities as they are at this point of the run (reference
+ * layout, tetrads concatenated, xyz interleaved: edmd_state_doubles() doubles each) and the per-tetrad
+ * observables obs[4n] = { E_ed[n] | (E_nb, E_el)[n] | temperature[n] } drain into the caller's (pinned)
+ * buffers while the engine goes on stepping.  Two tickets (0, 1) may be in flight; edmd_snapshot_wait blocks
+ * until a ticket's buffers are complete (callable from a writer thread).  NULL pointers are skipped. */
+int edmd_snapshot_begin(edmd_engine* e, int ticket, double* crd, double* vel, double* obs);
+int edmd_snapshot_wait(edmd_engine* e, int ticket);
+long long edmd_state_doubles(edmd_engine* e);
 /* edmd_step replays a CUDA graph of one step (on by default; off: plain kernel launches). */
 int edmd_set_graph(edmd_engine* e, int on);
 int edmd_sync(edmd_engine* e);

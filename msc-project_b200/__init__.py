@@ -10,4 +10,4 @@ The directory name contains a hyphen, so import it with
 """
 from .system import (EdmdSystem, ParamSet, config_params, make_gc90, make_ring, make_ragged,  # noqa: F401
                      TIMEFAC, BOLTZMANN, GENERATOR_SEED)
-from .engine import Engine, EngineError, load_library, library_path, Tetrad, build_tetrads  # noqa: F401
+from .engine import Engine, EngineGroup, EngineError, load_library, library_path, Tetrad, build_tetrads  # noqa: F401

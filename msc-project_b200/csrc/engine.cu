@@ -10,8 +10,10 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -77,6 +79,7 @@ struct edmd_engine {
     double *crd = nullptr, *vel = nullptr, *fed = nullptr, *rnd = nullptr, *fnb = nullptr;
     double* crd2 = nullptr;        // post-integrate coordinates written by the fused finish kernel
     bool latest_in_crd2 = false;   // owned tetrads' newest coordinates live in crd2 (see normalize())
+    double* obs = nullptr;         // one block [4n]: e_ed [n] | e_nb [n][2] | temp [n] (one peer mapping serves all three)
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     int* d_mark = nullptr;            // [2n+1] per-tetrad "in a flagged pair" flags, list counter, list of marked tetrads
     unsigned char* d_dirty = nullptr; // [n] fnb of this tetrad is non-zero from an earlier step
@@ -107,14 +110,33 @@ struct edmd_engine {
     void* d_cub_tmp = nullptr; size_t cub_tmp_bytes = 0; long long partners_cap = 0;
     int pair_builder = 0;   // 0 auto, 1 sweep (reference O(n^2)), 2 cell list
 
-    // peer-shared hit flags (fused scan + broadcast over NVLink): two buffers used by step parity,
-    // exported with CUDA IPC; peer_tbl[b][r] = rank r's buffer b as mapped into this process
-    unsigned long long* d_hitx[2] = {nullptr, nullptr};
+    // device-side CSR builder scratch (pairlist.cu: build_adjacency_device), grown on demand
+    int *d_adj_key = nullptr, *d_adj_key_sorted = nullptr;
+    unsigned long long *d_adj_val = nullptr, *d_adj_val_sorted = nullptr;
+    long long adj_rec_cap = 0;
+    double* d_bbox = nullptr;   // [7] centroid bounding box + finite flag
+
+    // ---- multi-GPU over peer memory (peer.cu) --------------------------------------------------------
+    // Every rank maps four buffers of every other rank: coordinates, velocities, the per-pair block masks
+    // the distance kernels publish into, the barrier flags, and the per-tetrad observables.  Between
+    // processes the mappings are CUDA IPC handles (edmd_peer_export / edmd_peer_attach); inside one process
+    // (edmd_group_*) they are the raw pointers with peer access enabled.
+    unsigned long long* d_hitx = nullptr;   // peer-visible mask buffer (replaces d_hit while peers are attached)
     long long hitx_cap = 0;
-    unsigned long long** d_peer_tbl = nullptr;   // device array [2][world]
-    std::vector<void*> peer_opened;
-    int world = 1, rank_id = 0, hit_parity = 0;
+    unsigned long long* d_flags = nullptr;  // [32] arrival counters written by the peers' barrier kernels
+    unsigned long long* d_epoch = nullptr;  // barrier number
+    int* d_peer_err = nullptr;              // set by a barrier that timed out
+    double** d_crd_tbl = nullptr;           // device arrays [world]: every rank's buffer as mapped here
+    unsigned long long** d_hit_tbl = nullptr;
+    unsigned long long** d_flag_tbl = nullptr;
+    std::vector<double*> peer_crd, peer_vel, peer_obs;   // host copies of the mapped pointers (own rank: local)
+    std::vector<void*> peer_opened;         // IPC mappings to close
+    int world = 1, rank_id = 0;
     bool peer_mode = false;
+    bool peer_replicated = false;           // every rank runs the per-tetrad kernels for all tetrads (small systems)
+    int* d_halo = nullptr; int* d_halo_count = nullptr; unsigned char* d_halo_flag = nullptr;
+    int halo_count = 0;                     // non-owned tetrads read by this rank's step
+    unsigned long long peer_timeout_ns = 60ull * 1000000000ull;
 
     // merge
     int* d_bp_off = nullptr;
@@ -149,6 +171,11 @@ struct edmd_engine {
     double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
     cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
     cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
+    // asynchronous output (edmd_snapshot_begin / _wait): device -> caller buffers on a side stream
+    cudaStream_t st_out = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_snap[2] = {nullptr, nullptr};
+    std::atomic<bool> snap_pending[2] = {{false}, {false}};   // cleared by edmd_snapshot_wait, possibly on a writer thread
+    double* d_obs_snap = nullptr;                   // [4n] copy of the observables taken in stream order
 };
 
 namespace {
@@ -185,7 +212,16 @@ void close_peers(edmd_engine* e);
 void free_system(edmd_engine* e) {
     drop_graph(e);
     close_peers(e);
-    cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
+    cudaFree(e->d_hitx); e->d_hitx = nullptr; e->hitx_cap = 0;
+    cudaFree(e->d_flags); cudaFree(e->d_epoch); cudaFree(e->d_peer_err);
+    e->d_flags = e->d_epoch = nullptr; e->d_peer_err = nullptr;
+    cudaFree(e->d_halo); cudaFree(e->d_halo_count); cudaFree(e->d_halo_flag);
+    e->d_halo = e->d_halo_count = nullptr; e->d_halo_flag = nullptr; e->halo_count = 0;
+    cudaFree(e->d_adj_key); cudaFree(e->d_adj_key_sorted); cudaFree(e->d_adj_val); cudaFree(e->d_adj_val_sorted);
+    e->d_adj_key = e->d_adj_key_sorted = nullptr; e->d_adj_val = e->d_adj_val_sorted = nullptr; e->adj_rec_cap = 0;
+    cudaFree(e->d_bbox); e->d_bbox = nullptr;
+    cudaFree(e->d_obs_snap); e->d_obs_snap = nullptr;
+    e->snap_pending[0] = e->snap_pending[1] = false;
     cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = nullptr; e->d_dirty = nullptr;
     cudaFree(e->d_perm); e->d_perm = nullptr;
@@ -203,7 +239,7 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_off3); cudaFree(e->d_avg); cudaFree(e->d_mass); cudaFree(e->d_chg);
     cudaFree(e->d_eval); cudaFree(e->d_evec);
     cudaFree(e->crd); cudaFree(e->crd2); cudaFree(e->vel); cudaFree(e->fed); cudaFree(e->rnd); cudaFree(e->fnb);
-    cudaFree(e->e_ed); cudaFree(e->e_nb); cudaFree(e->temp); cudaFree(e->cen); cudaFree(e->sup);
+    cudaFree(e->obs); e->obs = nullptr; cudaFree(e->cen); cudaFree(e->sup);
     cudaFree(e->d_stage); if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_row_count); cudaFree(e->d_row_off);
     cudaFree(e->d_adj_off); cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair); cudaFree(e->d_bp_off);
@@ -237,7 +273,9 @@ struct PtrKeyHash {
 };
 
 int ensure_pair_capacity(edmd_engine* e, long long np) {
-    close_peers(e);   // the driver re-establishes the peer-shared hit buffers after every rebuild
+    if (e->peer_mode && np > e->hitx_cap)
+        return fail(EDMD_ERR_STATE, "pair list of %lld pairs outgrew the peer-visible mask buffer (%lld): "
+                    "edmd_peer_detach on every rank, then export and attach again", np, e->hitx_cap);
     if (np <= e->pairs_cap) return 0;
     long long cap = std::max(np, e->pairs_cap * 3 / 2 + 1024);
     cudaFree(e->d_pairs); cudaFree(e->d_hit); cudaFree(e->d_pmask);
@@ -250,21 +288,11 @@ int ensure_pair_capacity(edmd_engine* e, long long np) {
     return 0;
 }
 
-// CSR over tetrads of the pair list, entries in pair-list order (worker.cpp:166-179 accumulates
-// in that order).  Host-side: runs every ntsync steps only.
-int build_adjacency(edmd_engine* e, const std::vector<int2>& pairs) {
-    const int n = e->n;
-    const long long np = (long long)pairs.size();
-    std::vector<long long> off(n + 1, 0);
-    for (long long p = 0; p < np; p++) { off[pairs[p].x + 1]++; off[pairs[p].y + 1]++; }
-    for (int t = 0; t < n; t++) off[t + 1] += off[t];
-    std::vector<int> partner((size_t)(2 * np) + 1), pidx((size_t)(2 * np) + 1);
-    std::vector<long long> cur(off.begin(), off.end() - 1);
-    for (long long p = 0; p < np; p++) {
-        const int a = pairs[p].x, b = pairs[p].y;
-        partner[cur[a]] = b;                       pidx[cur[a]++] = (int)p;
-        partner[cur[b]] = a | (int)0x80000000;     pidx[cur[b]++] = (int)p;
-    }
+// CSR over tetrads of the pair list, entries in pair-list order (worker.cpp:166-179 accumulates in that
+// order), built on the device from e->d_pairs (pairlist.cu).
+int build_adjacency(edmd_engine* e) {
+    const long long np = e->np;
+    if (np >= (1LL << 30)) return fail(EDMD_ERR_LIMIT, "%lld pairs exceeds the 2^30 limit of the adjacency builder", np);
     if (2 * np > e->adj_cap) {
         cudaFree(e->d_adj_partner); cudaFree(e->d_adj_pair);
         e->d_adj_partner = e->d_adj_pair = nullptr; e->adj_cap = 0;
@@ -273,12 +301,17 @@ int build_adjacency(edmd_engine* e, const std::vector<int2>& pairs) {
         CK(dev_alloc(&e->d_adj_pair, (size_t)cap));
         e->adj_cap = cap;
     }
-    CK(cudaMemcpyAsync(e->d_adj_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
-    if (np) {
-        CK(cudaMemcpyAsync(e->d_adj_partner, partner.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice, e->st));
-        CK(cudaMemcpyAsync(e->d_adj_pair, pidx.data(), sizeof(int) * 2 * np, cudaMemcpyHostToDevice, e->st));
+    if (2 * np > e->adj_rec_cap) {
+        cudaFree(e->d_adj_key); cudaFree(e->d_adj_key_sorted); cudaFree(e->d_adj_val); cudaFree(e->d_adj_val_sorted);
+        e->d_adj_key = e->d_adj_key_sorted = nullptr; e->d_adj_val = e->d_adj_val_sorted = nullptr; e->adj_rec_cap = 0;
+        const long long cap = 2 * np + np / 2 + 1024;
+        CK(dev_alloc(&e->d_adj_key, (size_t)cap)); CK(dev_alloc(&e->d_adj_key_sorted, (size_t)cap));
+        CK(dev_alloc(&e->d_adj_val, (size_t)cap)); CK(dev_alloc(&e->d_adj_val_sorted, (size_t)cap));
+        e->adj_rec_cap = cap;
     }
-    CK(cudaStreamSynchronize(e->st));
+    CK(build_adjacency_device(e->d_pairs, np, e->n, e->d_adj_key, e->d_adj_key_sorted, e->d_adj_val, e->d_adj_val_sorted,
+                              e->d_adj_off, e->d_adj_partner, e->d_adj_pair, &e->d_cub_tmp, &e->cub_tmp_bytes, e->st));
+    e->launches += np > 0 ? 4 : 1;
     return 0;
 }
 
@@ -293,11 +326,46 @@ int check_ready(edmd_engine* e, bool need_pairs) {
 void close_peers(edmd_engine* e) {
     for (void* p : e->peer_opened) cudaIpcCloseMemHandle(p);
     e->peer_opened.clear();
-    cudaFree(e->d_peer_tbl); e->d_peer_tbl = nullptr;
-    e->peer_mode = false;
+    cudaFree(e->d_crd_tbl); cudaFree(e->d_hit_tbl); cudaFree(e->d_flag_tbl);
+    e->d_crd_tbl = nullptr; e->d_hit_tbl = nullptr; e->d_flag_tbl = nullptr;
+    e->peer_crd.clear(); e->peer_vel.clear(); e->peer_obs.clear();
+    e->peer_mode = false; e->world = 1; e->rank_id = 0; e->halo_count = 0;
 }
 
-unsigned long long* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx[e->hit_parity] : e->d_hit; }
+unsigned long long* cur_hits(edmd_engine* e) { return e->peer_mode ? e->d_hitx : e->d_hit; }
+
+// flag barrier across the attached ranks, in stream order (peer.cu)
+int peer_barrier(edmd_engine* e) {
+    CK(launch_peer_barrier(e->d_flag_tbl, e->d_epoch, e->d_peer_err, e->world, e->rank_id, e->peer_timeout_ns, e->st));
+    e->launches++;
+    return 0;
+}
+int peer_check(edmd_engine* e) {   // after a synchronisation: did a barrier give up?
+    if (!e->peer_mode || !e->d_peer_err) return 0;
+    int bad = 0;
+    CK(cudaMemcpy(&bad, e->d_peer_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(EDMD_ERR_STATE, "a peer barrier timed out (rank %d of %d): a peer stopped stepping", e->rank_id, e->world);
+    return 0;
+}
+// the tetrads [a,b) that rank r owns: contiguous blocks of ceil(n/world), or everything when replicated
+void owned_range(const edmd_engine* e, int r, int* a, int* b) {
+    if (e->peer_replicated) { *a = 0; *b = e->n; return; }
+    const int chunk = (e->n + e->world - 1) / e->world;
+    *a = std::min(e->n, r * chunk); *b = std::min(e->n, *a + chunk);
+}
+// which non-owned tetrads a step of this rank reads (peer.cu); called whenever the shard or the list changes
+int rebuild_halo(edmd_engine* e) {
+    e->halo_count = 0;
+    if (!e->peer_mode || e->peer_replicated || !e->have_pairs) return 0;
+    if (!e->d_halo) {
+        CK(dev_alloc(&e->d_halo, (size_t)e->n)); CK(dev_alloc(&e->d_halo_count, 1)); CK(dev_alloc(&e->d_halo_flag, (size_t)e->n));
+    }
+    CK(build_halo_list(e->d_pairs, e->np, e->p0, e->p1, e->t0, e->t1, e->n, e->d_halo_flag, e->d_halo, e->d_halo_count, e->st));
+    CK(cudaMemcpyAsync(&e->halo_count, e->d_halo_count, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    e->launches += 2;
+    return 0;
+}
 
 void drop_graph(edmd_engine* e) {
     e->need_valid = false;   // every caller changes the pair list, the shard or the scan mode
@@ -357,7 +425,7 @@ int do_scan(edmd_engine* e) {
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
                                e->d_gb, e->d_pmask, e->d_param_id, e->d_perm, e->d_need,
-                               e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
+                               e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
         return 0;
@@ -365,7 +433,7 @@ int do_scan(edmd_engine* e) {
     timer_begin(e, T_SCAN);
     CK(launch_nb_scan(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->S,
                       nb_effective_cut2(e->sp), e->scan_mode, e->sms,
-                      e->peer_mode ? e->d_peer_tbl + (size_t)e->hit_parity * e->world : nullptr, e->world, e->st));
+                      e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
     timer_end(e, T_SCAN, e->p1 > e->p0 ? 1 : 0);
     e->hits_valid = true;
     return 0;
@@ -385,19 +453,21 @@ int do_finish(edmd_engine* e) {
     if (int rc = normalize(e)) return rc;
     if (!e->nb_clip) {   // unclipped forces requested: run the two unfused kernels
         if (int rc = do_accumulate(e)) return rc;
-        return do_integrate(e, 1, 1);
+        if (int rc = do_integrate(e, 1, 1)) return rc;
+    } else {
+        timer_begin(e, T_ACC);
+        CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
+                                  e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->ps, e->vel,
+                                  e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n,
+                                  e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
+        timer_end(e, T_ACC, e->np > 0 ? 4 : 1);
+        e->latest_in_crd2 = true;
     }
-    timer_begin(e, T_ACC);
-    CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
-                              e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->ps, e->vel,
-                              e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n,
-                              e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
-    timer_end(e, T_ACC, 3);
-    if (e->peer_mode) {   // this buffer is written again by the peers' scans two steps from now
-        CK(cudaMemsetAsync(e->d_hitx[e->hit_parity], 0, sizeof(unsigned long long) * (size_t)e->np, e->st));
-        e->hit_parity ^= 1;
-    }
-    e->latest_in_crd2 = true;
+    // Peer mode: the masks were stored by every rank's distance kernel; now that this rank has consumed them
+    // it clears the buffer.  The peers write into it again only after the next step's first barrier, which
+    // this rank joins after the memset (stream order).
+    if (e->peer_mode && e->np > 0)
+        CK(cudaMemsetAsync(e->d_hitx, 0, sizeof(unsigned long long) * (size_t)e->np, e->st));
     return 0;
 }
 // per-parameter-set table of Langevin noise amplitudes (rng.cu); depends on gamma, kT and dt
@@ -434,8 +504,16 @@ int do_integrate(edmd_engine* e, int do_vel, int do_crd) {
     return 0;
 }
 
+// a snapshot still draining to the host reads the staging buffer: whoever reuses it waits (in stream order)
+int snap_fence(edmd_engine* e) {
+    for (int k = 0; k < 2; k++)
+        if (e->snap_pending[k]) CK(cudaStreamWaitEvent(e->st, e->ev_snap[k], 0));
+    return 0;
+}
+
 // planes -> interleaved flat on the device (slot of d_stage), then to the pinned slot
 int stage_out(edmd_engine* e, const double* planes, int slot) {
+    if (int rc = snap_fence(e)) return rc;
     double* d = e->d_stage + (size_t)slot * e->total3;
     CK(launch_unpack_planes(planes, e->d_off3, e->d_natoms, d, e->n, e->S, e->st));
     e->launches++;
@@ -444,6 +522,7 @@ int stage_out(edmd_engine* e, const double* planes, int slot) {
     return 0;
 }
 int stage_in(edmd_engine* e, double* planes, int slot) {
+    if (int rc = snap_fence(e)) return rc;
     double* d = e->d_stage + (size_t)slot * e->total3;
     CK(cudaMemcpyAsync(d, e->h_stage + (size_t)slot * e->total3, sizeof(double) * e->total3,
                        cudaMemcpyHostToDevice, e->st));
@@ -492,6 +571,7 @@ void edmd_destroy(edmd_engine* e) {
     if (e->span0) { cudaEventDestroy(e->span0); cudaEventDestroy(e->span1); }
     for (cudaEvent_t ev : e->marks) cudaEventDestroy(ev);
     if (e->st_copy) cudaStreamDestroy(e->st_copy);
+    if (e->st_out) { cudaStreamDestroy(e->st_out); cudaEventDestroy(e->ev_staged); cudaEventDestroy(e->ev_snap[0]); cudaEventDestroy(e->ev_snap[1]); }
     if (e->ev_crd_in) { cudaEventDestroy(e->ev_crd_in); cudaEventDestroy(e->ev_vel_in); }
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
@@ -679,7 +759,8 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     const size_t planes = (size_t)n * 3 * S;
     CK(dev_alloc(&e->crd, planes)); CK(dev_alloc(&e->crd2, planes)); CK(dev_alloc(&e->vel, planes)); CK(dev_alloc(&e->fed, planes));
     CK(dev_alloc(&e->rnd, planes)); CK(dev_alloc(&e->fnb, planes));
-    CK(dev_alloc(&e->e_ed, n)); CK(dev_alloc(&e->e_nb, 2 * (size_t)n)); CK(dev_alloc(&e->temp, n));
+    CK(dev_alloc(&e->obs, 4 * (size_t)n));
+    e->e_ed = e->obs; e->e_nb = e->obs + n; e->temp = e->obs + 3 * (size_t)n;
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
     CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 2)); CK(dev_alloc(&e->d_dirty, (size_t)n));
     CK(dev_alloc(&e->d_gb, (size_t)n * 36));
@@ -701,9 +782,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(cudaMemcpyAsync(e->d_evec, evec.data(), sizeof(double) * evec.size(), cudaMemcpyHostToDevice, e->st));
     for (double* buf : {e->vel, e->fed, e->rnd, e->fnb})
         CK(cudaMemsetAsync(buf, 0, sizeof(double) * planes, e->st));
-    CK(cudaMemsetAsync(e->e_ed, 0, sizeof(double) * n, e->st));
-    CK(cudaMemsetAsync(e->e_nb, 0, sizeof(double) * 2 * n, e->st));
-    CK(cudaMemsetAsync(e->temp, 0, sizeof(double) * n, e->st));
+    CK(cudaMemsetAsync(e->obs, 0, sizeof(double) * 4 * n, e->st));
     CK(cudaStreamSynchronize(e->st));   // host vectors go out of scope
     e->rnd_zero = true;
 
@@ -745,6 +824,7 @@ int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n) {
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_state: n=%d but engine holds %d tetrads", n, e->n);
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
+    if (int rc = snap_fence(e)) return rc;
     timer_begin(e, T_LAYOUT);
     for (int which = 0; which < 2; which++) {
         double* planes = which ? e->vel : e->crd;
@@ -772,6 +852,7 @@ int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_state: n mismatch");
     CK(cudaSetDevice(e->device));
     if (int rc = normalize(e)) return rc;
+    if (int rc = snap_fence(e)) return rc;
     bool dense[2];
     for (int which = 0; which < 2; which++) {
         dense[which] = dense_field(e, tets, which);
@@ -888,21 +969,18 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     timer_begin(e, T_PAIRS);
     CK(launch_centroids(e->crd, e->d_natoms, e->cen, n, e->S, e->st));
 
-    // builder choice: the cell list pays off when the cutoff is small against the extent
+    // builder choice: the cell list pays off when the cutoff is small against the extent.  Only the bounding
+    // box (7 doubles) and the pair count cross PCIe; sums, offsets and the adjacency stay on the device.
     bool cells = false;
     CellGridHost grid{};
     if (e->pair_builder != 1 && e->sp.mole_cutoff > 0.0 && e->sp.mole_cutoff < 1e8) {
-        std::vector<double> cen(4 * (size_t)n);
-        CK(cudaMemcpyAsync(cen.data(), e->cen, sizeof(double) * cen.size(), cudaMemcpyDeviceToHost, e->st));
+        if (!e->d_bbox) CK(dev_alloc(&e->d_bbox, 8));
+        CK(launch_centroid_bbox(e->cen, n, e->d_bbox, e->st));
+        double bb[7];
+        CK(cudaMemcpyAsync(bb, e->d_bbox, sizeof(bb), cudaMemcpyDeviceToHost, e->st));
         CK(cudaStreamSynchronize(e->st));
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        bool finite = true;
-        for (int t = 0; t < n; t++)
-            for (int c = 0; c < 3; c++) {
-                const double v = cen[4 * (size_t)t + c];
-                if (!(v > -1e15 && v < 1e15)) finite = false;
-                lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v);
-            }
+        const double* lo = bb; const double* hi = bb + 3;
+        const bool finite = bb[6] != 0.0;
         const double h = e->sp.mole_cutoff;
         const double ncell = finite ? (floor((hi[0] - lo[0]) / h) + 1) * (floor((hi[1] - lo[1]) / h) + 1) *
                                           (floor((hi[2] - lo[2]) / h) + 1) : 0.0;
@@ -920,14 +998,12 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     if (cells) CK(launch_cell_rows(e->cen, n, cut2, e->sp.mole_least, grid, e->d_cell_sorted, e->d_tet_sorted,
                                    e->d_row_count, nullptr, nullptr, 0, e->st));
     else CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, nullptr, nullptr, 0, e->st));
-    std::vector<long long> cnt(n), off(n + 1, 0);
-    CK(cudaMemcpyAsync(cnt.data(), e->d_row_count, sizeof(long long) * n, cudaMemcpyDeviceToHost, e->st));
+    CK(scan_row_counts(e->d_row_count, e->d_row_off, n, &e->d_cub_tmp, &e->cub_tmp_bytes, e->st));
+    long long np = 0;
+    CK(cudaMemcpyAsync(&np, e->d_row_off + n, sizeof(long long), cudaMemcpyDeviceToHost, e->st));
     CK(cudaStreamSynchronize(e->st));
-    for (int i = 0; i < n; i++) off[i + 1] = off[i] + cnt[i];
-    const long long np = off[n];
     if (np >= (1LL << 31)) return fail(EDMD_ERR_LIMIT, "%lld pairs exceeds the 2^31 pair-index limit", np);
     if (int rc = ensure_pair_capacity(e, np)) return rc;
-    CK(cudaMemcpyAsync(e->d_row_off, off.data(), sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, e->st));
     if (cells) {
         if (np > e->partners_cap) {
             cudaFree(e->d_partners); cudaFree(e->d_partners_sorted);
@@ -943,14 +1019,14 @@ int edmd_build_pairlist(edmd_engine* e, long long* num_pairs) {
     } else {
         CK(launch_pair_rows(e->cen, n, cut2, e->sp.mole_least, e->d_row_count, e->d_row_off, e->d_pairs, 1, e->st));
     }
-    timer_end(e, T_PAIRS, cells ? 6 : 3);
-    std::vector<int2> pairs((size_t)np);
-    if (np) CK(cudaMemcpyAsync(pairs.data(), e->d_pairs, sizeof(int2) * np, cudaMemcpyDeviceToHost, e->st));
-    CK(cudaStreamSynchronize(e->st));
     e->np = np;
-    if (int rc = build_adjacency(e, pairs)) return rc;
+    if (int rc = build_adjacency(e)) return rc;
+    timer_end(e, T_PAIRS, cells ? 9 : 5);
     e->have_pairs = true; e->hits_valid = false; drop_graph(e);
     if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
+    else { e->p0 = std::min(e->p0, np); e->p1 = std::min(e->p1, np); }
+    if (e->peer_mode && np > 0) CK(cudaMemsetAsync(e->d_hitx, 0, sizeof(unsigned long long) * (size_t)np, e->st));
+    if (int rc = rebuild_halo(e)) return rc;
     if (num_pairs) *num_pairs = np;
     return 0;
 }
@@ -980,10 +1056,13 @@ int edmd_set_pairlist(edmd_engine* e, const int* pairs, long long np) {
     if (int rc = ensure_pair_capacity(e, np)) return rc;
     if (np) CK(cudaMemcpy(e->d_pairs, pv.data(), sizeof(int2) * np, cudaMemcpyHostToDevice));
     e->np = np;
-    if (int rc = build_adjacency(e, pv)) return rc;
+    if (int rc = build_adjacency(e)) return rc;
+    CK(cudaStreamSynchronize(e->st));
     e->have_pairs = true; e->hits_valid = false; drop_graph(e);
     if (!e->shard_pairs_custom) { e->p0 = 0; e->p1 = np; }
-    return 0;
+    else { e->p0 = std::min(e->p0, np); e->p1 = std::min(e->p1, np); }
+    if (e->peer_mode && np > 0) CK(cudaMemsetAsync(e->d_hitx, 0, sizeof(unsigned long long) * (size_t)np, e->st));
+    return rebuild_halo(e);
 }
 
 int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
@@ -996,8 +1075,9 @@ int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
     drop_graph(e);
     e->t0 = t0; e->t1 = t1; e->p0 = p0; e->p1 = p1; e->shard_pairs_custom = true;
     e->hits_valid = false;
-    if (range_changed) return upload_order(e);
-    return 0;
+    e->peer_replicated = (t0 == 0 && t1 == e->n);
+    if (range_changed) if (int rc = upload_order(e)) return rc;
+    return rebuild_halo(e);
 }
 
 int edmd_ed_forces(edmd_engine* e) {
@@ -1101,11 +1181,22 @@ int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
     return 0;
 }
 
+// One step on this rank.  With peers attached the two exchange points of the path are (1) after the ED pass,
+// when every owner's re-embedded coordinates exist: barrier, then pull the non-owned tetrads this rank reads;
+// (2) after the distance pass, whose kernels stored their masks into every rank's buffer: barrier, then the
+// owners' force pass.  Both are kernels on the engine stream, so the whole sharded step is graph-captured.
 static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     if (int rc = do_ed(e)) return rc;
     if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
     if (random_mode == 1 && calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
+    if (e->peer_mode && !e->peer_replicated) {
+        if (int rc = peer_barrier(e)) return rc;
+        CK(launch_halo_pull(e->crd, e->d_crd_tbl, e->d_halo, e->halo_count, (e->n + e->world - 1) / e->world, e->S,
+                            e->sms, e->st));
+        if (e->halo_count) e->launches++;
+    }
     if (int rc = do_scan(e)) return rc;
+    if (e->peer_mode) if (int rc = peer_barrier(e)) return rc;
     return do_finish(e);
 }
 
@@ -1120,7 +1211,7 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
     if (int rc = check_ready(e, true)) return rc;
     if (random_mode != 0 && random_mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown", random_mode);
     CK(cudaSetDevice(e->device));
-    const bool graph_ok = e->use_graph && !e->timing && e->nb_clip && !e->peer_mode && nsteps >= 1;
+    const bool graph_ok = e->use_graph && !e->timing && e->nb_clip && nsteps >= 1;
     if (!graph_ok) {
         for (int it = 0; it < nsteps; it++) {
             if (int rc = one_step(e, random_mode, nullptr)) return rc;
@@ -1177,8 +1268,10 @@ int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int ran
     if (int rc = check_ready(e, true)) return rc;
     if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_step_host: n=%d but engine holds %d tetrads", n, e->n);
     if (nsteps < 1) return fail(EDMD_ERR_ARG, "edmd_step_host: nsteps must be >= 1");
+    if (e->peer_mode) return fail(EDMD_ERR_STATE, "edmd_step_host runs on a single-GPU engine; with peers attached use "
+                                  "edmd_set_state / edmd_step / edmd_peer_gather / edmd_get_state");
     if (random_mode != 0 && random_mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown", random_mode);
-    const bool pipelined = dense_field(e, tets, 0) && dense_field(e, tets, 1) && e->nb_clip && !e->peer_mode && !e->timing;
+    const bool pipelined = dense_field(e, tets, 0) && dense_field(e, tets, 1) && e->nb_clip && !e->timing;
     if (!pipelined) {
         if (int rc = edmd_set_state(e, tets, n)) return rc;
         if (int rc = edmd_step(e, nsteps, random_mode)) return rc;
@@ -1191,6 +1284,7 @@ int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int ran
         CK(cudaEventCreateWithFlags(&e->ev_vel_in, cudaEventDisableTiming));
     }
     e->latest_in_crd2 = false;                       // the device state is replaced as a whole
+    if (int rc = snap_fence(e)) return rc;
     const size_t bytes = sizeof(double) * e->total3;
     CK(cudaMemcpyAsync(e->d_stage, tets[0].coordinates, bytes, cudaMemcpyHostToDevice, e->st));
     CK(cudaEventRecord(e->ev_crd_in, e->st));
@@ -1213,11 +1307,54 @@ int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int ran
     return edmd_get_state(e, tets, n);
 }
 
+// Asynchronous output (north_star: "trajectory output stays host-side on a side stream"; replaces the blocking
+// copies around Master::write_Info / write_Crds, master.cpp:388-419).  The state is unpacked to the reference
+// layout in stream order (so it is the state at this point of the run), then drains to the caller's buffers on
+// a second stream while the engine stream goes on stepping.
+int edmd_snapshot_begin(edmd_engine* e, int ticket, double* crd, double* vel, double* obs) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (ticket < 0 || ticket > 1) return fail(EDMD_ERR_ARG, "snapshot ticket must be 0 or 1");
+    if (e->snap_pending[ticket]) return fail(EDMD_ERR_STATE, "snapshot %d is still in flight: call edmd_snapshot_wait first", ticket);
+    CK(cudaSetDevice(e->device));
+    if (!e->st_out) {
+        CK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_staged, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_snap[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_snap[1], cudaEventDisableTiming));
+    }
+    if (int rc = normalize(e)) return rc;
+    if (int rc = snap_fence(e)) return rc;      // the other ticket may still be reading the staging buffer
+    if (crd) { CK(launch_unpack_planes(e->crd, e->d_off3, e->d_natoms, e->d_stage, e->n, e->S, e->st)); e->launches++; }
+    if (vel) { CK(launch_unpack_planes(e->vel, e->d_off3, e->d_natoms, e->d_stage + e->total3, e->n, e->S, e->st)); e->launches++; }
+    if (obs) {
+        if (!e->d_obs_snap) CK(dev_alloc(&e->d_obs_snap, 4 * (size_t)e->n));
+        CK(cudaMemcpyAsync(e->d_obs_snap, e->obs, sizeof(double) * 4 * e->n, cudaMemcpyDeviceToDevice, e->st));
+    }
+    CK(cudaEventRecord(e->ev_staged, e->st));
+    CK(cudaStreamWaitEvent(e->st_out, e->ev_staged, 0));
+    if (crd) CK(cudaMemcpyAsync(crd, e->d_stage, sizeof(double) * e->total3, cudaMemcpyDeviceToHost, e->st_out));
+    if (vel) CK(cudaMemcpyAsync(vel, e->d_stage + e->total3, sizeof(double) * e->total3, cudaMemcpyDeviceToHost, e->st_out));
+    if (obs) CK(cudaMemcpyAsync(obs, e->d_obs_snap, sizeof(double) * 4 * e->n, cudaMemcpyDeviceToHost, e->st_out));
+    CK(cudaEventRecord(e->ev_snap[ticket], e->st_out));
+    e->snap_pending[ticket] = true;
+    return 0;
+}
+
+int edmd_snapshot_wait(edmd_engine* e, int ticket) {
+    if (!e || ticket < 0 || ticket > 1) return fail(EDMD_ERR_ARG, "bad snapshot ticket");
+    if (!e->snap_pending[ticket]) return 0;
+    CK(cudaEventSynchronize(e->ev_snap[ticket]));
+    e->snap_pending[ticket] = false;
+    return 0;
+}
+
+long long edmd_state_doubles(edmd_engine* e) { return e ? e->total3 : 0; }
+
 int edmd_sync(edmd_engine* e) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->st));
-    return 0;
+    return peer_check(e);
 }
 
 int edmd_device_buffer(edmd_engine* e, int which, void** dptr, size_t* bytes) {
@@ -1350,58 +1487,147 @@ void* edmd_alloc_pinned(size_t bytes) {
 }
 void edmd_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
-int edmd_peer_hits_export(edmd_engine* e, unsigned char* handles /* 2 x 64 bytes */) {
-    if (int rc = check_ready(e, true)) return rc;
-    if (!handles) return fail(EDMD_ERR_ARG, "null handle buffer");
+// ---- multi-GPU: attaching peers ---------------------------------------------------------------------
+namespace {
+
+struct PeerPtrs { double* crd; double* vel; unsigned long long* hitx; unsigned long long* flags; double* obs; };
+
+// allocate (or keep) the peer-visible buffers of this engine and reset the barrier state
+int peer_prepare(edmd_engine* e) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->st));
     close_peers(e);
-    const long long need = std::max<long long>(e->np, 1);
+    const long long need = std::max<long long>(std::max<long long>(2 * e->np, 16LL * e->n), 4096);
     if (need > e->hitx_cap) {
-        cudaFree(e->d_hitx[0]); cudaFree(e->d_hitx[1]); e->d_hitx[0] = e->d_hitx[1] = nullptr; e->hitx_cap = 0;
-        const long long cap = need + need / 2 + 4096;
-        CK(cudaMalloc((void**)&e->d_hitx[0], sizeof(unsigned long long) * (size_t)cap)); CK(cudaMalloc((void**)&e->d_hitx[1], sizeof(unsigned long long) * (size_t)cap));
-        e->hitx_cap = cap;
+        cudaFree(e->d_hitx); e->d_hitx = nullptr; e->hitx_cap = 0;
+        CK(cudaMalloc((void**)&e->d_hitx, sizeof(unsigned long long) * (size_t)need));
+        e->hitx_cap = need;
     }
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    for (int b = 0; b < 2; b++) {
-        CK(cudaMemset(e->d_hitx[b], 0, sizeof(unsigned long long) * (size_t)e->hitx_cap));
-        cudaIpcMemHandle_t h;
-        CK(cudaIpcGetMemHandle(&h, e->d_hitx[b]));
-        memcpy(handles + 64 * b, &h, 64);
+    if (!e->d_flags) {
+        CK(cudaMalloc((void**)&e->d_flags, sizeof(unsigned long long) * 32));
+        CK(cudaMalloc((void**)&e->d_epoch, sizeof(unsigned long long)));
+        CK(cudaMalloc((void**)&e->d_peer_err, sizeof(int)));
+    }
+    CK(cudaMemset(e->d_hitx, 0, sizeof(unsigned long long) * (size_t)e->hitx_cap));
+    CK(cudaMemset(e->d_flags, 0, sizeof(unsigned long long) * 32));
+    CK(cudaMemset(e->d_epoch, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(e->d_peer_err, 0, sizeof(int)));
+    if (const char* t = getenv("EDMD_PEER_TIMEOUT_S")) {
+        const double sec = atof(t);
+        if (sec > 0.0) e->peer_timeout_ns = (unsigned long long)(sec * 1e9);
     }
     return 0;
 }
 
-int edmd_peer_hits_open(edmd_engine* e, const unsigned char* all_handles /* world x 2 x 64 */, int world, int rank) {
-    if (int rc = check_ready(e, true)) return rc;
-    if (!all_handles || world < 1 || world > 32 || rank < 0 || rank >= world || !e->d_hitx[0])
-        return fail(EDMD_ERR_ARG, "edmd_peer_hits_open: bad arguments (export first; world <= 32)");
-    CK(cudaSetDevice(e->device));
-    close_peers(e);
-    std::vector<unsigned long long*> tbl(2 * (size_t)world, nullptr);
-    for (int r = 0; r < world; r++)
-        for (int b = 0; b < 2; b++) {
-            if (r == rank) { tbl[(size_t)b * world + r] = e->d_hitx[b]; continue; }
-            cudaIpcMemHandle_t h;
-            memcpy(&h, all_handles + ((size_t)r * 2 + b) * 64, 64);
-            void* p = nullptr;
-            CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-            e->peer_opened.push_back(p);
-            tbl[(size_t)b * world + r] = (unsigned long long*)p;
-        }
-    CK(cudaMalloc((void**)&e->d_peer_tbl, sizeof(unsigned long long*) * tbl.size()));
-    CK(cudaMemcpy(e->d_peer_tbl, tbl.data(), sizeof(unsigned long long*) * tbl.size(), cudaMemcpyHostToDevice));
-    e->world = world; e->rank_id = rank; e->hit_parity = 0; e->peer_mode = true;
+// install the tables of mapped pointers (own rank: the local buffers)
+int peer_install(edmd_engine* e, const std::vector<PeerPtrs>& all, int world, int rank) {
+    std::vector<double*> crd(world);
+    std::vector<unsigned long long*> hit(world), flg(world);
+    e->peer_crd.assign(world, nullptr); e->peer_vel.assign(world, nullptr); e->peer_obs.assign(world, nullptr);
+    for (int r = 0; r < world; r++) {
+        crd[r] = all[r].crd; hit[r] = all[r].hitx; flg[r] = all[r].flags;
+        e->peer_crd[r] = all[r].crd; e->peer_vel[r] = all[r].vel; e->peer_obs[r] = all[r].obs;
+    }
+    CK(cudaMalloc((void**)&e->d_crd_tbl, sizeof(double*) * world));
+    CK(cudaMalloc((void**)&e->d_hit_tbl, sizeof(unsigned long long*) * world));
+    CK(cudaMalloc((void**)&e->d_flag_tbl, sizeof(unsigned long long*) * world));
+    CK(cudaMemcpy(e->d_crd_tbl, crd.data(), sizeof(double*) * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_hit_tbl, hit.data(), sizeof(unsigned long long*) * world, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_flag_tbl, flg.data(), sizeof(unsigned long long*) * world, cudaMemcpyHostToDevice));
+    e->world = world; e->rank_id = rank; e->peer_mode = true;
+    e->peer_replicated = (e->t0 == 0 && e->t1 == e->n);
     drop_graph(e);
+    return rebuild_halo(e);
+}
+
+// every rank's owned coordinates / velocities / observables -> this rank's buffers (contiguous owner blocks:
+// plain device-to-device copies through the mappings).  Collective: barrier before (owners have finished
+// writing) and after (nobody overwrites what a peer is still copying).
+int peer_gather(edmd_engine* e, int what) {
+    if (!e->peer_mode) return 0;
+    if (int rc = normalize(e)) return rc;
+    if (int rc = peer_barrier(e)) return rc;
+    if (!e->peer_replicated) {
+        const size_t w3 = 3 * (size_t)e->S;
+        for (int r = 0; r < e->world; r++) {
+            if (r == e->rank_id) continue;
+            int a, b; owned_range(e, r, &a, &b);
+            if (b <= a) continue;
+            const size_t off = (size_t)a * w3, cnt = (size_t)(b - a) * w3;
+            if (what & 1) CK(cudaMemcpyAsync(e->crd + off, e->peer_crd[r] + off, sizeof(double) * cnt, cudaMemcpyDefault, e->st));
+            if (what & 2) CK(cudaMemcpyAsync(e->vel + off, e->peer_vel[r] + off, sizeof(double) * cnt, cudaMemcpyDefault, e->st));
+            if (what & 4) {
+                const size_t n = (size_t)e->n;
+                CK(cudaMemcpyAsync(e->obs + a, e->peer_obs[r] + a, sizeof(double) * (b - a), cudaMemcpyDefault, e->st));
+                CK(cudaMemcpyAsync(e->obs + n + 2 * (size_t)a, e->peer_obs[r] + n + 2 * (size_t)a, sizeof(double) * 2 * (b - a), cudaMemcpyDefault, e->st));
+                CK(cudaMemcpyAsync(e->obs + 3 * n + a, e->peer_obs[r] + 3 * n + a, sizeof(double) * (b - a), cudaMemcpyDefault, e->st));
+            }
+        }
+    }
+    return peer_barrier(e);
+}
+
+}  // namespace
+
+/* blob = five CUDA IPC handles: coordinates, velocities, mask buffer, barrier flags, observables */
+int edmd_peer_export(edmd_engine* e, unsigned char* blob) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!blob) return fail(EDMD_ERR_ARG, "null blob");
+    if (int rc = normalize(e)) return rc;
+    if (int rc = peer_prepare(e)) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    static_assert(EDMD_PEER_BLOB_BYTES == 5 * 64, "blob layout");
+    void* bufs[5] = {e->crd, e->vel, e->d_hitx, e->d_flags, e->obs};
+    for (int k = 0; k < 5; k++) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, bufs[k]));
+        memcpy(blob + 64 * k, &h, 64);
+    }
     return 0;
 }
 
-int edmd_peer_hits_close(edmd_engine* e) {
+int edmd_peer_attach(edmd_engine* e, const unsigned char* blobs, int world, int rank) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!blobs || world < 1 || world > 32 || rank < 0 || rank >= world || !e->d_hitx)
+        return fail(EDMD_ERR_ARG, "edmd_peer_attach: bad arguments (call edmd_peer_export first; world <= 32)");
+    CK(cudaSetDevice(e->device));
+    std::vector<PeerPtrs> all(world);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { all[r] = PeerPtrs{e->crd, e->vel, e->d_hitx, e->d_flags, e->obs}; continue; }
+        void* p[5];
+        for (int k = 0; k < 5; k++) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, blobs + (size_t)r * EDMD_PEER_BLOB_BYTES + 64 * k, 64);
+            p[k] = nullptr;
+            CK(cudaIpcOpenMemHandle(&p[k], h, cudaIpcMemLazyEnablePeerAccess));
+            e->peer_opened.push_back(p[k]);
+        }
+        all[r] = PeerPtrs{(double*)p[0], (double*)p[1], (unsigned long long*)p[2], (unsigned long long*)p[3], (double*)p[4]};
+    }
+    return peer_install(e, all, world, rank);
+}
+
+int edmd_peer_detach(edmd_engine* e) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->st));
+    const int rc = peer_check(e);
     close_peers(e);
+    drop_graph(e);
+    return rc;
+}
+
+int edmd_peer_gather(edmd_engine* e, int what) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (what < 1 || what > 7) return fail(EDMD_ERR_ARG, "edmd_peer_gather: what must be a combination of 1 (coordinates), 2 (velocities), 4 (observables)");
+    CK(cudaSetDevice(e->device));
+    return peer_gather(e, what);
+}
+
+int edmd_world(edmd_engine* e, int* world, int* rank) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    if (world) *world = e->peer_mode ? e->world : 1;
+    if (rank) *rank = e->peer_mode ? e->rank_id : 0;
     return 0;
 }
 
@@ -1411,6 +1637,204 @@ int edmd_measure_fp64_peak(int device, double* tflops, double* sm_mhz_est) {
         return fail(EDMD_ERR_CUDA, "no CUDA device available");
     CK(cudaSetDevice(device));
     CK(measure_fp64_peak(tflops, sm_mhz_est));
+    return 0;
+}
+
+// ---- single process, several GPUs ------------------------------------------------------------------
+}  // extern "C" (reopened below)
+
+struct edmd_group {
+    std::vector<edmd_engine*> eng;
+    bool attached = false;
+    int replicate_max = 0;     // systems up to this size run the per-tetrad kernels on every GPU (0: never)
+};
+
+namespace {
+
+int group_attach(edmd_group* g) {
+    const int world = (int)g->eng.size();
+    for (edmd_engine* e : g->eng) {
+        CK(cudaSetDevice(e->device));
+        if (int rc = normalize(e)) return rc;
+        if (int rc = peer_prepare(e)) return rc;
+    }
+    std::vector<PeerPtrs> all(world);
+    for (int r = 0; r < world; r++) {
+        edmd_engine* e = g->eng[r];
+        all[r] = PeerPtrs{e->crd, e->vel, e->d_hitx, e->d_flags, e->obs};
+    }
+    for (int r = 0; r < world; r++) {
+        CK(cudaSetDevice(g->eng[r]->device));
+        if (int rc = peer_install(g->eng[r], all, world, r)) return rc;
+    }
+    g->attached = true;
+    return 0;
+}
+
+int group_detach(edmd_group* g) {
+    for (edmd_engine* e : g->eng) {
+        CK(cudaSetDevice(e->device));
+        CK(cudaStreamSynchronize(e->st));
+    }
+    for (edmd_engine* e : g->eng) { close_peers(e); drop_graph(e); }
+    g->attached = false;
+    return 0;
+}
+
+// enqueue the collective on every GPU before anything waits for one of them
+int group_gather(edmd_group* g, int what) {
+    if (!g->attached) return 0;
+    for (edmd_engine* e : g->eng) {
+        CK(cudaSetDevice(e->device));
+        if (int rc = peer_gather(e, what)) return rc;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int edmd_group_create(const edmd_params* p, int n_gpus, const int* devices, edmd_group** out) {
+    if (!out) return fail(EDMD_ERR_ARG, "out is null");
+    *out = nullptr;
+    if (n_gpus < 1 || n_gpus > 32) return fail(EDMD_ERR_ARG, "n_gpus = %d out of range [1,32]", n_gpus);
+    edmd_group* g = new edmd_group();
+    for (int r = 0; r < n_gpus; r++) {
+        edmd_engine* e = nullptr;
+        if (int rc = edmd_create(p, devices ? devices[r] : r, &e)) { edmd_group_destroy(g); return rc; }
+        g->eng.push_back(e);
+    }
+    // every GPU reads and writes every other GPU's buffers directly (NVLink / NVSwitch)
+    for (int a = 0; a < n_gpus; a++)
+        for (int b = 0; b < n_gpus; b++) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g->eng[a]->device, g->eng[b]->device);
+            if (!can) {
+                const int da = g->eng[a]->device, db = g->eng[b]->device;
+                edmd_group_destroy(g);
+                return fail(EDMD_ERR_CUDA, "device %d cannot access device %d's memory: no peer path", da, db);
+            }
+            cudaSetDevice(g->eng[a]->device);
+            cudaError_t err = cudaDeviceEnablePeerAccess(g->eng[b]->device, 0);
+            if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); err = cudaSuccess; }
+            if (err != cudaSuccess) {
+                edmd_group_destroy(g);
+                return fail(EDMD_ERR_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(err));
+            }
+        }
+    *out = g;
+    return 0;
+}
+
+void edmd_group_destroy(edmd_group* g) {
+    if (!g) return;
+    if (g->attached) group_detach(g);
+    for (edmd_engine* e : g->eng) edmd_destroy(e);
+    delete g;
+}
+
+int edmd_group_size(edmd_group* g) { return g ? (int)g->eng.size() : 0; }
+edmd_engine* edmd_group_engine(edmd_group* g, int rank) {
+    return (g && rank >= 0 && rank < (int)g->eng.size()) ? g->eng[rank] : nullptr;
+}
+
+int edmd_group_upload_tetrads(edmd_group* g, const edmd_tetrad* tets, int n, const int* bp_atoms) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    if (g->attached) if (int rc = group_detach(g)) return rc;
+    for (edmd_engine* e : g->eng) if (int rc = edmd_upload_tetrads(e, tets, n, bp_atoms)) return rc;
+    return 0;
+}
+
+int edmd_group_set_state(edmd_group* g, const edmd_tetrad* tets, int n) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    for (edmd_engine* e : g->eng) if (int rc = edmd_set_state(e, tets, n)) return rc;
+    return 0;
+}
+
+int edmd_group_get_state(edmd_group* g, edmd_tetrad* tets, int n) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    if (int rc = group_gather(g, 3)) return rc;
+    return edmd_get_state(g->eng[0], tets, n);
+}
+
+int edmd_group_set_rng(edmd_group* g, long time0, int rank, long calls_before) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    for (edmd_engine* e : g->eng) if (int rc = edmd_set_rng(e, time0, rank, calls_before)) return rc;
+    return 0;
+}
+
+int edmd_group_build_pairlist(edmd_group* g, long long* num_pairs) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    const int world = (int)g->eng.size();
+    if (int rc = group_gather(g, 1)) return rc;        // the list is built from everybody's coordinates
+    long long np = -1;
+    bool regrow = false;
+    for (edmd_engine* e : g->eng) {
+        long long mine = 0;
+        const int rc = edmd_build_pairlist(e, &mine);
+        if (rc == EDMD_ERR_STATE && g->attached) { regrow = true; break; }
+        if (rc) return rc;
+        if (np >= 0 && mine != np) return fail(EDMD_ERR_STATE, "GPUs disagree on the pair list: %lld vs %lld pairs", mine, np);
+        np = mine;
+    }
+    if (regrow) {   // the list outgrew the peer-visible mask buffers: map larger ones
+        if (int rc = group_detach(g)) return rc;
+        np = -1;
+        for (edmd_engine* e : g->eng) {
+            long long mine = 0;
+            if (int rc = edmd_build_pairlist(e, &mine)) return rc;
+            np = mine;
+        }
+    }
+    if (world > 1 && !g->attached) if (int rc = group_attach(g)) return rc;
+    // work split: contiguous tetrad blocks, equal pair slices (generate_Indexes, master.cpp:214-242)
+    const int n = g->eng[0]->n;
+    const bool replicate = n <= g->replicate_max;
+    const int tchunk = (n + world - 1) / world;
+    const long long pchunk = (np + world - 1) / world;
+    for (int r = 0; r < world; r++) {
+        const int t0 = replicate ? 0 : std::min(n, r * tchunk), t1 = replicate ? n : std::min(n, t0 + tchunk);
+        const long long p0 = std::min(np, r * pchunk), p1 = std::min(np, p0 + pchunk);
+        if (int rc = edmd_set_shard(g->eng[r], t0, t1, p0, p1)) return rc;
+    }
+    if (num_pairs) *num_pairs = np;
+    return 0;
+}
+
+int edmd_group_step(edmd_group* g, int nsteps, int random_mode) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    for (edmd_engine* e : g->eng) if (int rc = edmd_step(e, nsteps, random_mode)) return rc;
+    return 0;
+}
+
+int edmd_group_merge(edmd_group* g) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    if (int rc = group_gather(g, 3)) return rc;
+    for (edmd_engine* e : g->eng) if (int rc = edmd_merge(e)) return rc;
+    return 0;
+}
+
+int edmd_group_get_energies(edmd_group* g, double out[4]) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    if (int rc = group_gather(g, 4)) return rc;
+    return edmd_get_energies(g->eng[0], out);
+}
+
+int edmd_group_snapshot_begin(edmd_group* g, int ticket, double* crd, double* vel, double* obs) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    if (int rc = group_gather(g, (crd ? 1 : 0) | (vel ? 2 : 0) | (obs ? 4 : 0))) return rc;
+    return edmd_snapshot_begin(g->eng[0], ticket, crd, vel, obs);
+}
+int edmd_group_snapshot_wait(edmd_group* g, int ticket) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    return edmd_snapshot_wait(g->eng[0], ticket);
+}
+
+int edmd_group_sync(edmd_group* g) {
+    if (!g) return fail(EDMD_ERR_ARG, "null group");
+    for (edmd_engine* e : g->eng) if (int rc = edmd_sync(e)) return rc;
     return 0;
 }
 

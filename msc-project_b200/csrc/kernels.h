@@ -66,6 +66,22 @@ cudaError_t launch_cell_rows(const double* cen, int n, double cut2, double least
 cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const long long* row_off, int n,
                                long long np, int2* pairs, void** tmp, size_t* tmp_bytes, cudaStream_t st);
 
+// device-side bookkeeping of a pair-list rebuild (pairlist.cu)
+cudaError_t launch_centroid_bbox(const double* cen, int n, double* out7, cudaStream_t st);
+cudaError_t scan_row_counts(const long long* row_count, long long* row_off, int n, void** tmp, size_t* tmp_bytes,
+                            cudaStream_t st);
+cudaError_t build_adjacency_device(const int2* pairs, long long np, int n, int* key, int* key_sorted,
+                                   unsigned long long* val, unsigned long long* val_sorted, long long* adj_off,
+                                   int* adj_partner, int* adj_pair, void** tmp, size_t* tmp_bytes, cudaStream_t st);
+
+// multi-GPU exchange over peer memory (peer.cu)
+cudaError_t launch_peer_barrier(unsigned long long* const* flags, unsigned long long* epoch, int* err, int world,
+                                int rank, unsigned long long timeout_ns, cudaStream_t st);
+cudaError_t launch_halo_pull(double* local, double* const* peer, const int* list, int count, int chunk, int S, int sms,
+                             cudaStream_t st);
+cudaError_t build_halo_list(const int2* pairs, long long np, long long p0, long long p1, int t0, int t1, int n,
+                            unsigned char* flag, int* list, int* count, cudaStream_t st);
+
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,

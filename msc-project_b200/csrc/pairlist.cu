@@ -15,6 +15,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_segmented_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace edmd {
 
@@ -201,6 +202,120 @@ cudaError_t sort_rows_and_emit(const int* partners, int* partners_sorted, const 
     int grid = (n + wpb - 1) / wpb;
     if (grid > 148 * 16) grid = 148 * 16;
     rows_to_pairs_kernel<<<grid, wpb * 32, 0, st>>>(partners_sorted, row_off, n, pairs);
+    return cudaGetLastError();
+}
+
+// ---- device-side bookkeeping of a rebuild (nothing but three scalars crosses PCIe) -------------------
+static cudaError_t grow_tmp(void** tmp, size_t* tmp_bytes, size_t need) {
+    if (need <= *tmp_bytes) return cudaSuccess;
+    cudaFree(*tmp);
+    cudaError_t err = cudaMalloc(tmp, need);
+    if (err != cudaSuccess) { *tmp = nullptr; *tmp_bytes = 0; return err; }
+    *tmp_bytes = need;
+    return cudaSuccess;
+}
+
+// Bounding box of the centroids: out = {lo x,y,z, hi x,y,z, all finite ? 1 : 0}.  One CTA; n <= a few 1e6.
+__global__ void __launch_bounds__(1024) centroid_bbox_kernel(const double* cen, int n, double* out) {
+    __shared__ double slo[3][32], shi[3][32];
+    __shared__ int sbad[32];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    int bad = 0;
+    for (int t = threadIdx.x; t < n; t += blockDim.x)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double v = cen[4 * (size_t)t + c];
+            if (!(v > -1e15 && v < 1e15)) bad = 1;
+            lo[c] = fmin(lo[c], v); hi[c] = fmax(hi[c], v);
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) { for (int c = 0; c < 3; c++) { slo[c][warp] = lo[c]; shi[c][warp] = hi[c]; } sbad[warp] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int w = 1; w < nw; w++) {
+            for (int c = 0; c < 3; c++) { lo[c] = fmin(lo[c], slo[c][w]); hi[c] = fmax(hi[c], shi[c][w]); }
+            bad |= sbad[w];
+        }
+        for (int c = 0; c < 3; c++) { out[c] = lo[c]; out[3 + c] = hi[c]; }
+        out[6] = bad ? 0.0 : 1.0;
+    }
+}
+cudaError_t launch_centroid_bbox(const double* cen, int n, double* out7, cudaStream_t st) {
+    centroid_bbox_kernel<<<1, 1024, 0, st>>>(cen, n, out7);
+    return cudaGetLastError();
+}
+
+// row_off[0] = 0, row_off[i+1] = sum of row_count[0..i]
+cudaError_t scan_row_counts(const long long* row_count, long long* row_off, int n, void** tmp, size_t* tmp_bytes,
+                            cudaStream_t st) {
+    cudaError_t err = cudaMemsetAsync(row_off, 0, sizeof(long long), st);
+    if (err != cudaSuccess) return err;
+    size_t need = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, need, row_count, row_off + 1, n, st);
+    if ((err = grow_tmp(tmp, tmp_bytes, need)) != cudaSuccess) return err;
+    return cub::DeviceScan::InclusiveSum(*tmp, need, row_count, row_off + 1, n, st);
+}
+
+// CSR over tetrads of the pair list, entries of a tetrad in pair-list order (worker.cpp:166-179 accumulates
+// in that order): every pair contributes two (tetrad, 2*pair + side) records, a STABLE radix sort by tetrad
+// keeps each tetrad's records in ascending pair order.
+__global__ void adj_records_kernel(const int2* pairs, long long np, int* key, unsigned long long* val) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+        const int2 pr = pairs[p];
+        key[2 * p] = pr.x;     val[2 * p] = (unsigned long long)p << 1;
+        key[2 * p + 1] = pr.y; val[2 * p + 1] = ((unsigned long long)p << 1) | 1ull;
+    }
+}
+__global__ void adj_emit_kernel(const unsigned long long* val_sorted, const int2* pairs, long long total,
+                                int* adj_partner, int* adj_pair) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const unsigned long long v = val_sorted[e];
+        const long long p = (long long)(v >> 1);
+        const int2 pr = pairs[p];
+        adj_pair[e] = (int)p;
+        adj_partner[e] = (v & 1ull) ? (pr.x | (int)0x80000000) : pr.y;   // bit 31: this tetrad is t2 of the pair
+    }
+}
+__global__ void adj_offsets_kernel(const int* key_sorted, long long total, int n, long long* adj_off) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n) return;
+    long long lo = 0, hi = total;
+    while (lo < hi) { const long long mid = (lo + hi) >> 1; if (key_sorted[mid] < t) lo = mid + 1; else hi = mid; }
+    adj_off[t] = lo;
+}
+cudaError_t build_adjacency_device(const int2* pairs, long long np, int n, int* key, int* key_sorted,
+                                   unsigned long long* val, unsigned long long* val_sorted, long long* adj_off,
+                                   int* adj_partner, int* adj_pair, void** tmp, size_t* tmp_bytes, cudaStream_t st) {
+    const long long total = 2 * np;
+    if (np > 0) {
+        long long blocks = (np + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        adj_records_kernel<<<(int)blocks, 256, 0, st>>>(pairs, np, key, val);
+        int bits = 1;
+        while ((1LL << bits) < (long long)n) bits++;
+        size_t need = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, key, key_sorted, val, val_sorted, total, 0, bits, st);
+        cudaError_t err = grow_tmp(tmp, tmp_bytes, need);
+        if (err != cudaSuccess) return err;
+        err = cub::DeviceRadixSort::SortPairs(*tmp, need, key, key_sorted, val, val_sorted, total, 0, bits, st);
+        if (err != cudaSuccess) return err;
+        long long eb = (total + 255) / 256;
+        if (eb > 148 * 16) eb = 148 * 16;
+        adj_emit_kernel<<<(int)eb, 256, 0, st>>>(val_sorted, pairs, total, adj_partner, adj_pair);
+    }
+    adj_offsets_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(key_sorted, total, n, adj_off);
     return cudaGetLastError();
 }
 

@@ -1,5 +1,12 @@
 """Multi-GPU driver: one process per GPU, torch.distributed for the plumbing.
 
+With the GPU engine the per-step exchanges do NOT go through this file: ``ShardedEngine`` exchanges the
+engines' CUDA IPC handles once (``edmd_peer_export`` / ``edmd_peer_attach``), sets the shard, and from then on
+``step`` is one ``edmd_step`` call per rank — barriers, halo pull and mask broadcast are kernels inside the
+engine's CUDA graph (csrc/peer.cu, csrc/engine.cu).  The torch-collective protocol below is the same
+decomposition spelled out with all-gathers; it is what runs on CPU (gloo, world_size 2) with the oracle
+standing in for the engine, and what any backend without peer memory would use.
+
 Replaces the reference's MPI master/worker decomposition
 (/root/reference/src/master.cpp:214-292 generate_Indexes / send_Workload_Indexes /
 calculate_Forces, src/worker.cpp:109-187, src/mpilib.cpp): there is no master.  Every rank
@@ -168,9 +175,15 @@ class EngineBackend:
     def merge(self): self.e.merge()
     def build_pairlist(self): return self.e.build_pairlist()
     def get_pairlist(self): return self.e.get_pairlist()
-    def peer_hits_export(self): return self.e.peer_hits_export()
-    def peer_hits_open(self, handles, world, rank): self.e.peer_hits_open(handles, world, rank)
     def sync(self): self.e.sync()
+
+    # in-engine multi-GPU (peer memory)
+    def peer_export(self): return self.e.peer_export()
+    def peer_attach(self, blobs, world, rank): self.e.peer_attach(blobs, world, rank)
+    def peer_detach(self): self.e.peer_detach()
+    def peer_gather(self, what): self.e.peer_gather(what)
+    def engine_step(self, nsteps, random_mode): self.e.step(nsteps, random_mode)
+    def engine_set_rng(self, time0, rank, calls): self.e.set_rng(time0, rank, calls)
 
 
 # Below this size the per-tetrad kernels are replicated on every rank instead of exchanging
@@ -183,16 +196,17 @@ class ShardedEngine:
     """Runs the reference step protocol (simulation.cpp:34-55) over world_size ranks."""
 
     def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None, replicate=None,
-                 halo=None, peer_hits=None):
+                 halo=None, native=None):
         self.b, self.dist, self.n, self.rank, self.world, self.group = backend, dist, n_tetrads, rank, world, group
-        self.replicate = (n_tetrads <= REPLICATE_MAX_TETRADS) if replicate is None else bool(replicate)
+        # native: the engine itself runs the sharded step over peer memory (GPU engine, world > 1)
+        self.native = (hasattr(backend, "peer_export") and world > 1) if native is None else bool(native)
+        if replicate is None:
+            replicate = False if self.native else n_tetrads <= REPLICATE_MAX_TETRADS
+        self.replicate = bool(replicate)
         # halo: sparse exchange of the tetrad blocks actually read (default for large systems)
         self.halo = (not self.replicate) if halo is None else (bool(halo) and not self.replicate)
         self.halo_plan = None
-        # fused scan + hit broadcast over peer memory (needs a backend with CUDA IPC: the GPU engine)
-        self.peer_hits = (hasattr(backend, "peer_hits_export") and world > 1) if peer_hits is None else bool(peer_hits)
-        self._peer_on = False
-        self._token = None
+        self._attached = False
         self.plan = None
         self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
 
@@ -237,11 +251,6 @@ class ShardedEngine:
         self._all_gather_blocks(self.b.vel_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
 
     def gather_hits(self):
-        if self._peer_on:
-            # the scan kernel has already stored its hits into every rank's buffer over NVLink;
-            # what is left of the collective is the barrier before anyone reads them
-            self.dist.all_reduce(self._token, group=self.group)
-            return
         self._all_gather_blocks(self.b.hit_tensor(), 1, self.plan.np, self.plan.p_chunk)
 
     @property
@@ -252,7 +261,8 @@ class ShardedEngine:
     def build_pairlist(self) -> int:
         """Every rank builds the same list from the same (gathered) coordinates — the list is
         a pure function of the centroids, so no exchange is needed (master.cpp:180-210)."""
-        t0, t1, _ = block_range(self.n, self.world, self.rank)
+        if self.native:
+            return self._build_native()
         self.b.set_shard(0, self.n, 0, 0)
         npairs = self.b.build_pairlist()
         self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
@@ -268,25 +278,59 @@ class ShardedEngine:
             import torch
             with self.b.stream_ctx():
                 self.halo_plan = hp.exchange_lists(self.dist, torch, dev, self.group)
-        self._peer_on = False
-        if self.peer_hits and self.world > 1 and npairs > 0:
-            mine = self.b.peer_hits_export()
-            every = [None] * self.world
-            self.dist.all_gather_object(every, mine, group=self.group)
-            self.b.peer_hits_open(b"".join(every), self.world, self.rank)
-            if self._token is None:
-                import torch
-                self._token = torch.zeros(1, dtype=torch.int32, device=self.b.crd_tensor().device)
-            self.dist.barrier(group=self.group)     # every rank's buffers are zeroed and mapped
-            self._peer_on = True
-            if hasattr(self.b, "invalidate"):
-                self.b.invalidate()
         return npairs
+
+    # -- in-engine path ------------------------------------------------------------------
+    def _attach(self):
+        blob = self.b.peer_export()
+        every = [None] * self.world
+        self.dist.all_gather_object(every, blob, group=self.group)
+        self.b.peer_attach(b"".join(every), self.world, self.rank)
+        self.dist.barrier(group=self.group)      # every rank has mapped every buffer
+        self._attached = True
+
+    def _detach(self):
+        if self._attached:
+            self.dist.barrier(group=self.group)  # nobody is still stepping into a buffer about to be unmapped
+            self.b.peer_detach()
+            self.dist.barrier(group=self.group)
+            self._attached = False
+
+    def _build_native(self) -> int:
+        if self._attached:
+            self.b.peer_gather(1)                # owners' coordinates -> every rank
+        try:
+            npairs = self.b.build_pairlist()
+        except RuntimeError as err:              # the list outgrew the peer-visible mask buffer (same on every rank)
+            if not (self._attached and "outgrew" in str(err)):
+                raise
+            self._detach()
+            npairs = self.b.build_pairlist()
+        if not self._attached:
+            self._attach()
+        self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
+        if self.replicate:
+            self.plan.t0, self.plan.t1 = 0, self.n
+        self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)
+        self.b.engine_set_rng(self.time0, self.rng_rank, self.calls)
+        return npairs
+
+    def close(self):
+        """Unmap the peers (collective); call before destroying the engines."""
+        if self.native:
+            self._detach()
 
     def set_rng(self, time0, rank, calls):
         self.time0, self.rng_rank, self.calls = time0, rank, calls
+        if self.native:
+            self.b.engine_set_rng(time0, rank, calls)
 
     def step(self, nsteps=1, random_mode=0):
+        if self.native:                          # one call: the sharded step is inside the engine
+            self.b.engine_step(nsteps, random_mode)
+            if random_mode == 1:
+                self.calls += nsteps * self.n
+            return
         with self.b.stream_ctx():
             for _ in range(nsteps):
                 self.b.ed_forces()
@@ -304,6 +348,10 @@ class ShardedEngine:
 
     def merge(self):
         """4-fold overlap average needs neighbours' copies: gather state, merge everywhere."""
+        if self.native:
+            self.b.peer_gather(3)
+            self.b.merge()
+            return
         with self.b.stream_ctx():
             self.gather_coordinates(full=True)
             self.gather_velocities()
@@ -311,6 +359,10 @@ class ShardedEngine:
 
     def finish(self):
         """Make every rank's copy of coordinates and velocities complete (for output)."""
+        if self.native:
+            self.b.peer_gather(7)
+            self.b.sync()
+            return
         with self.b.stream_ctx():
             self.gather_coordinates(full=True)
             self.gather_velocities()

@@ -87,9 +87,29 @@ def load_library():
         "edmd_get_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
         "edmd_set_pairlist": (C.c_int, [E, C.POINTER(C.c_int), LL]),
         "edmd_set_shard": (C.c_int, [E, C.c_int, C.c_int, LL, LL]),
-        "edmd_peer_hits_export": (C.c_int, [E, C.c_char_p]),
-        "edmd_peer_hits_open": (C.c_int, [E, C.c_char_p, C.c_int, C.c_int]),
-        "edmd_peer_hits_close": (C.c_int, [E]),
+        "edmd_peer_export": (C.c_int, [E, C.c_char_p]),
+        "edmd_peer_attach": (C.c_int, [E, C.c_char_p, C.c_int, C.c_int]),
+        "edmd_peer_detach": (C.c_int, [E]),
+        "edmd_peer_gather": (C.c_int, [E, C.c_int]),
+        "edmd_world": (C.c_int, [E, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "edmd_group_create": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_int), C.POINTER(E)]),
+        "edmd_group_destroy": (None, [E]),
+        "edmd_group_size": (C.c_int, [E]),
+        "edmd_group_engine": (E, [E, C.c_int]),
+        "edmd_group_upload_tetrads": (C.c_int, [E, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+        "edmd_group_set_state": (C.c_int, [E, C.c_void_p, C.c_int]),
+        "edmd_group_get_state": (C.c_int, [E, C.c_void_p, C.c_int]),
+        "edmd_group_set_rng": (C.c_int, [E, C.c_long, C.c_int, C.c_long]),
+        "edmd_group_build_pairlist": (C.c_int, [E, C.POINTER(LL)]),
+        "edmd_group_step": (C.c_int, [E, C.c_int, C.c_int]),
+        "edmd_group_merge": (C.c_int, [E]),
+        "edmd_group_get_energies": (C.c_int, [E, PD]),
+        "edmd_group_sync": (C.c_int, [E]),
+        "edmd_group_snapshot_begin": (C.c_int, [E, C.c_int, PD, PD, PD]),
+        "edmd_group_snapshot_wait": (C.c_int, [E, C.c_int]),
+        "edmd_snapshot_begin": (C.c_int, [E, C.c_int, PD, PD, PD]),
+        "edmd_snapshot_wait": (C.c_int, [E, C.c_int]),
+        "edmd_state_doubles": (LL, [E]),
         "edmd_ed_forces": (C.c_int, [E]),
         "edmd_random_terms": (C.c_int, [E, C.c_int, C.c_long, C.c_int, C.c_long]),
         "edmd_nb_forces": (C.c_int, [E]),
@@ -343,16 +363,25 @@ class Engine:
     def set_nb_scan_mode(self, mode: int):
         self._ck(self.lib.edmd_set_nb_scan_mode(self.h, mode))
 
-    def peer_hits_export(self) -> bytes:
-        buf = C.create_string_buffer(128)
-        self._ck(self.lib.edmd_peer_hits_export(self.h, buf))
+    PEER_BLOB_BYTES = 320
+    GATHER_CRD, GATHER_VEL, GATHER_OBS = 1, 2, 4
+
+    def peer_export(self) -> bytes:
+        """IPC handles of this engine's peer-visible buffers (edmd_peer_export)."""
+        buf = C.create_string_buffer(self.PEER_BLOB_BYTES)
+        self._ck(self.lib.edmd_peer_export(self.h, buf))
         return buf.raw
 
-    def peer_hits_open(self, all_handles: bytes, world: int, rank: int):
-        self._ck(self.lib.edmd_peer_hits_open(self.h, all_handles, world, rank))
+    def peer_attach(self, all_blobs: bytes, world: int, rank: int):
+        self._ck(self.lib.edmd_peer_attach(self.h, all_blobs, world, rank))
 
-    def peer_hits_close(self):
-        self._ck(self.lib.edmd_peer_hits_close(self.h))
+    def peer_detach(self):
+        self._ck(self.lib.edmd_peer_detach(self.h))
+
+    def peer_gather(self, what: int = 3):
+        """Collective (every rank calls it): complete this rank's copy of coordinates (1), velocities (2),
+        per-tetrad energies and temperatures (4)."""
+        self._ck(self.lib.edmd_peer_gather(self.h, what))
 
     def ed_forces(self):
         self._ck(self.lib.edmd_ed_forces(self.h))
@@ -455,6 +484,68 @@ class Engine:
         c = C.c_longlong()
         self._ck(self.lib.edmd_nb_stats(self.h, C.byref(c)))
         return c.value
+
+
+class EngineGroup:
+    """edmd_group_*: one process driving several GPUs (what the C++ driver `edmddna --gpus N` uses)."""
+
+    def __init__(self, sys: EdmdSystem, n_gpus: int, devices=None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        p = Params(*[float(x) for x in sys.params])
+        dev = None
+        if devices is not None:
+            self._dev = (C.c_int * n_gpus)(*devices)
+            dev = self._dev
+        self._ck(self.lib.edmd_group_create(C.byref(p), n_gpus, dev, C.byref(self.h)))
+        self.sys = sys
+        self.block = build_tetrads(sys, pinned=False)
+        bp = None
+        if sys.bp_atoms is not None:
+            self._bp = np.ascontiguousarray(sys.bp_atoms, dtype=np.int32)
+            bp = self._bp.ctypes.data_as(C.POINTER(C.c_int))
+        self._ck(self.lib.edmd_group_upload_tetrads(self.h, self.block.ptr, sys.n, bp))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(f"edmd_b200 error {rc}: {self.lib.edmd_last_error().decode()}")
+
+    def close(self):
+        if self.h:
+            self.lib.edmd_group_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build_pairlist(self) -> int:
+        npairs = C.c_longlong()
+        self._ck(self.lib.edmd_group_build_pairlist(self.h, C.byref(npairs)))
+        return npairs.value
+
+    def set_rng(self, time0=1000000000, rank=1, calls_before=0):
+        self._ck(self.lib.edmd_group_set_rng(self.h, time0, rank, calls_before))
+
+    def step(self, nsteps=1, random_mode=0):
+        self._ck(self.lib.edmd_group_step(self.h, nsteps, random_mode))
+
+    def merge(self):
+        self._ck(self.lib.edmd_group_merge(self.h))
+
+    def get_state(self):
+        self._ck(self.lib.edmd_group_get_state(self.h, self.block.ptr, self.sys.n))
+        return self.block.crd.copy(), self.block.vel.copy()
+
+    def energies(self) -> np.ndarray:
+        out = np.zeros(4)
+        self._ck(self.lib.edmd_group_get_energies(self.h, _ptr(out)))
+        return out
+
+    def sync(self):
+        self._ck(self.lib.edmd_group_sync(self.h))
 
 
 def _nb_stats(self) -> dict:

@@ -3,15 +3,28 @@
 // engine.  Reads the reference's unmodified input deck (config.txt, .prm, .crd) and writes its
 // energies / trajectory / restart files in the same formats.
 //
-//   edmddna [--config ./config.txt] [--gpu 0] [--random 1|0] [--time T] [--nsteps N]
+//   edmddna [--config ./config.txt] [--gpus N] [--gpu D] [--random 1|0] [--time T] [--nsteps N]
 //
+// --gpus N   run on N GPUs of this box (one process; replaces `aprun -n 91`, edmddna.pbs:20): tetrads and
+//            the pair list are sharded over the GPUs, which exchange through peer memory (edmd_group_*).
+// --gpu D    first device ordinal (default 0).
 // --random 0 switches the Langevin random terms off (the reference has no such switch);
-// --time T pins the time(NULL) term of the random seed (edmd.cpp:179) for reproducible runs.
+// --time T   pins the time(NULL) term of the random seed (edmd.cpp:179) for reproducible runs.
+//
+// Output is off the step loop's critical path: at an output point the merged state is unpacked on the
+// device and drains into one of two pinned host buffers on a side stream (edmd_snapshot_begin) while the
+// next block of steps is already running; a writer thread waits for the copy, rebuilds the per-base-pair
+// arrays Master keeps (master.cpp:357-382) and writes the files (io.cpp:292-383).  The files are
+// byte-identical to the blocking version.
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <iostream>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "edmd.hpp"
@@ -25,20 +38,125 @@ static void check(int rc, const char* what) {
     if (rc) { std::cerr << ">>> ERROR: " << what << ": " << edmd_last_error() << std::endl; std::exit(1); }
 }
 
+namespace {
+
+struct OutputJob { int ticket, istep; bool info, crd; };
+
+// Two pinned snapshot buffers + the thread that turns them into files, in submission order.
+class Writer {
+public:
+    Writer(IO* io, edmd_group* grp, long long state_doubles, int n)
+        : io_(io), grp_(grp), n_(n), total_(state_doubles), stop_(false) {
+        for (int k = 0; k < 2; k++) {
+            crd_[k] = (double*)edmd_alloc_pinned(sizeof(double) * (size_t)total_);
+            vel_[k] = (double*)edmd_alloc_pinned(sizeof(double) * (size_t)total_);
+            obs_[k] = (double*)edmd_alloc_pinned(sizeof(double) * 4 * (size_t)n_);
+            if (!crd_[k] || !vel_[k] || !obs_[k]) check(-2, "edmd_alloc_pinned");
+            busy_[k] = false;
+        }
+        flat_crd_.resize(3 * (size_t)io->crd.total_Atoms);
+        flat_vel_.resize(3 * (size_t)io->crd.total_Atoms);
+        thread_ = std::thread(&Writer::run, this);
+    }
+    ~Writer() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        thread_.join();
+        for (int k = 0; k < 2; k++) { edmd_free_pinned(crd_[k]); edmd_free_pinned(vel_[k]); edmd_free_pinned(obs_[k]); }
+    }
+    // called from the step loop: start the device -> host copy of the current state and queue the file work
+    void submit(int istep, bool info, bool crd) {
+        const int k = next_;
+        next_ ^= 1;
+        {   // the buffer's previous contents must be on disk before the copy engine overwrites them
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return !busy_[k]; });
+            busy_[k] = true;
+        }
+        check(edmd_group_snapshot_begin(grp_, k, crd_[k], vel_[k], info ? obs_[k] : nullptr), "edmd_group_snapshot_begin");
+        { std::lock_guard<std::mutex> lk(mu_); jobs_.push_back(OutputJob{k, istep, info, crd}); }
+        cv_.notify_all();
+    }
+    void drain() {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return jobs_.empty() && !busy_[0] && !busy_[1]; });
+    }
+
+private:
+    void run() {
+        for (;;) {
+            OutputJob job;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+                if (jobs_.empty()) return;
+                job = jobs_.front();
+            }
+            check(edmd_group_snapshot_wait(grp_, job.ticket), "edmd_group_snapshot_wait");
+            const int k = job.ticket;
+            // flat per-base-pair arrays as Master keeps them (master.cpp:357-382): after the merge all copies
+            // of a base pair agree, so a plain scatter in tetrad order reproduces them
+            size_t off = 0;
+            for (int t = 0; t < n_; t++) {
+                const int n3 = 3 * io_->tetrad[t].num_Atoms;
+                std::memcpy(&flat_crd_[io_->displs[t]], crd_[k] + off, sizeof(double) * n3);
+                std::memcpy(&flat_vel_[io_->displs[t]], vel_[k] + off, sizeof(double) * n3);
+                off += n3;
+            }
+            if (job.info) {                                                    // Master::write_Info
+                // master.cpp:393-401: sequential sums in tetrad order, mean temperature
+                const double* o = obs_[k];
+                double e[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int t = 0; t < n_; t++) {
+                    e[0] += o[t]; e[1] += o[n_ + 2 * (size_t)t]; e[2] += o[n_ + 2 * (size_t)t + 1]; e[3] += o[3 * (size_t)n_ + t];
+                }
+                e[3] /= n_;
+                io_->write_Energies(job.istep + io_->ntsync, e);
+                io_->write_Trajectory(job.istep, io_->displs[io_->crd.num_BP - 3], flat_crd_.data());
+            }
+            if (job.crd) io_->update_Crd_File(flat_vel_.data(), flat_crd_.data());   // Master::write_Crds
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                jobs_.pop_front();
+                busy_[k] = false;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    IO* io_;
+    edmd_group* grp_;
+    int n_;
+    long long total_;
+    double *crd_[2], *vel_[2], *obs_[2];
+    bool busy_[2];
+    int next_ = 0;
+    std::vector<double> flat_crd_, flat_vel_;
+    std::deque<OutputJob> jobs_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_;
+    std::thread thread_;
+};
+
+}  // namespace
+
 int main(int argc, char** argv) {
     IO io;
     EDMD edmd;
-    int gpu = 0, random_mode = 1, nsteps_override = -1;
+    int gpu = 0, gpus = 1, random_mode = 1, nsteps_override = -1;
     long seed_time = (long)std::time(0);
     for (int i = 1; i < argc; i++) {
         const bool more = i + 1 < argc;
         if (!std::strcmp(argv[i], "--config") && more) io.config_File = argv[++i];
         else if (!std::strcmp(argv[i], "--gpu") && more) gpu = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--gpus") && more) gpus = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--random") && more) random_mode = std::atoi(argv[++i]) ? 1 : 0;
         else if (!std::strcmp(argv[i], "--time") && more) seed_time = std::atol(argv[++i]);
         else if (!std::strcmp(argv[i], "--nsteps") && more) nsteps_override = std::atoi(argv[++i]);
-        else { std::cerr << "usage: edmddna [--config F] [--gpu D] [--random 0|1] [--time T] [--nsteps N]\n"; return 2; }
+        else { std::cerr << "usage: edmddna [--config F] [--gpus N] [--gpu D] [--random 0|1] [--time T] [--nsteps N]\n"; return 2; }
     }
+    if (gpus < 1) { std::cerr << "--gpus must be >= 1\n"; return 2; }
     const clock_t start = std::clock();
 
     // Master::initialise, master.cpp:55-109
@@ -64,41 +182,30 @@ int main(int argc, char** argv) {
 
     edmd_params p = {edmd.dt, edmd.gamma, edmd.tautp, edmd.temperature, edmd.scaled,
                      edmd.mole_Cutoff, edmd.atom_Cutoff, edmd.mole_Least};
-    edmd_engine* eng = 0;
-    check(edmd_create(&p, gpu, &eng), "edmd_create");
-    check(edmd_upload_tetrads(eng, reinterpret_cast<edmd_tetrad*>(io.tetrad), n, io.crd.BP_Atoms), "edmd_upload_tetrads");
-    check(edmd_set_rng(eng, seed_time, /*rank of the single worker*/ 1, 0), "edmd_set_rng");
+    std::vector<int> devices(gpus);
+    for (int r = 0; r < gpus; r++) devices[r] = gpu + r;
+    edmd_group* grp = 0;
+    check(edmd_group_create(&p, gpus, devices.data(), &grp), "edmd_group_create");
+    check(edmd_group_upload_tetrads(grp, reinterpret_cast<edmd_tetrad*>(io.tetrad), n, io.crd.BP_Atoms), "edmd_group_upload_tetrads");
+    check(edmd_group_set_rng(grp, seed_time, /*rank of the single worker*/ 1, 0), "edmd_group_set_rng");
+    std::cout << ">>> GPUs: " << gpus << std::endl;
 
-    std::vector<double> coordinates(3 * (size_t)io.crd.total_Atoms), velocities(3 * (size_t)io.crd.total_Atoms);
-    std::cout << "Simulation starting..." << std::endl;
-
-    for (int istep = 0; istep < io.nsteps; istep += io.ntsync) {          // simulation.cpp:34-55
-        std::cout << "istep: " << istep << std::endl;
-        long long npairs = 0;
-        check(edmd_build_pairlist(eng, &npairs), "edmd_build_pairlist");   // generate_Pair_Lists
-        check(edmd_step(eng, io.ntsync, random_mode), "edmd_step");        // ntsync x (forces, velocity, coordinate)
-        check(edmd_merge(eng), "edmd_merge");                              // merge_Vels_n_Crds
-        const bool want_info = istep % io.ntwt == 0, want_crd = istep % io.ntpr == 0;
-        if (want_info || want_crd) {
-            check(edmd_get_state(eng, reinterpret_cast<edmd_tetrad*>(io.tetrad), n), "edmd_get_state");
-            // flat per-base-pair arrays as Master keeps them (master.cpp:357-382): after the merge
-            // all copies of a base pair agree, so a plain scatter reproduces them
-            for (int t = 0; t < n; t++)
-                for (int k = 0; k < 3 * io.tetrad[t].num_Atoms; k++) {
-                    coordinates[io.displs[t] + k] = io.tetrad[t].coordinates[k];
-                    velocities[io.displs[t] + k] = io.tetrad[t].velocities[k];
-                }
+    {
+        Writer writer(&io, grp, edmd_state_doubles(edmd_group_engine(grp, 0)), n);
+        std::cout << "Simulation starting..." << std::endl;
+        for (int istep = 0; istep < io.nsteps; istep += io.ntsync) {          // simulation.cpp:34-55
+            std::cout << "istep: " << istep << std::endl;
+            long long npairs = 0;
+            check(edmd_group_build_pairlist(grp, &npairs), "edmd_group_build_pairlist");   // generate_Pair_Lists
+            check(edmd_group_step(grp, io.ntsync, random_mode), "edmd_group_step");        // ntsync x (forces, velocity, coordinate)
+            check(edmd_group_merge(grp), "edmd_group_merge");                              // merge_Vels_n_Crds
+            const bool want_info = istep % io.ntwt == 0, want_crd = istep % io.ntpr == 0;
+            if (want_info || want_crd) writer.submit(istep, want_info, want_crd);           // write_Info / write_Crds
         }
-        if (want_info) {                                                   // Master::write_Info
-            double e[4];
-            check(edmd_get_energies(eng, e), "edmd_get_energies");
-            io.write_Energies(istep + io.ntsync, e);
-            io.write_Trajectory(istep, io.displs[io.crd.num_BP - 3], coordinates.data());
-        }
-        if (want_crd) io.update_Crd_File(velocities.data(), coordinates.data());   // Master::write_Crds
+        check(edmd_group_sync(grp), "edmd_group_sync");
+        writer.drain();
     }
-    check(edmd_sync(eng), "edmd_sync");
-    edmd_destroy(eng);
+    edmd_group_destroy(grp);
     std::cout << "Simulation ended.\nTime usage of simualtion: " << double(std::clock() - start) / CLOCKS_PER_SEC
               << std::endl << std::endl;
     return 0;

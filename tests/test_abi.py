@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol(edmd):
     assert len(names) >= 40
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/edmd_b200.h but not exported"
-    assert lib.edmd_abi_version() == 1
+    assert lib.edmd_abi_version() == 2
 
 
 def test_python_binding_covers_the_header(edmd):

@@ -1,32 +1,43 @@
-"""torchrun tools/dist_perf.py N_TETRADS [mode] : step time of the sharded engine (mode: halo|allgather|replicate)."""
-import importlib, os, sys, time
+"""[torchrun] tools/dist_perf.py N_TETRADS [steps random_mode kind laps lap_gap qfac] : step time of the (sharded) engine.
+The timed steps run as the engine runs them in production (one CUDA graph per step, in-engine barriers);
+a second short pass with the per-phase timers on gives the breakdown."""
+import importlib, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np, torch, torch.distributed as dist
+import numpy as np, torch
 pkg = importlib.import_module("msc-project_b200"); dmod = importlib.import_module("msc-project_b200.dist")
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
+dist = None
 if world > 1:
+    import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-n = int(sys.argv[1]); mode = sys.argv[2] if len(sys.argv) > 2 else "halo"; steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
-random_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-scan_mode = int(sys.argv[5]) if len(sys.argv) > 5 else 1
-s = pkg.make_ring(n, kind="ring")
+a = sys.argv[1:]
+n = int(a[0]); steps = int(a[1]) if len(a) > 1 else 20; random_mode = int(a[2]) if len(a) > 2 else 1
+kind = a[3] if len(a) > 3 else "ring"; laps = int(a[4]) if len(a) > 4 else 2; gap = float(a[5]) if len(a) > 5 else 40.0
+qfac = float(a[6]) if len(a) > 6 else 0.0
+s = pkg.make_ring(n, kind=kind, laps=laps, lap_gap=gap)
 g = pkg.Engine(s, device=local)
-g.set_nb_scan_mode(scan_mode)
-sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist if world > 1 else None, s.n, rank, world,
-                        replicate=(mode == "replicate"), halo=(mode == "halo"))
+g.set_nb_consts(100.0, qfac)
+sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
+sh.set_rng(1000000000, 1, 0)
 t0 = time.time(); npairs = sh.build_pairlist(); tb = time.time() - t0
 sh.step(3, random_mode); g.sync()
-if world > 1: dist.barrier()
-g.timing(True); g.timing_reset()
-g.mark(0); sh.step(steps, random_mode); g.mark(1)
+if dist: dist.barrier()
+g.mark(0); t0 = time.perf_counter(); sh.step(steps, random_mode); t_host = time.perf_counter() - t0; g.mark(1)
 ms = g.mark_elapsed(0, 1) / steps
 t = torch.tensor([ms], device=f"cuda:{local}", dtype=torch.float64)
-if world > 1: dist.all_reduce(t, op=dist.ReduceOp.MAX)
-k = {nm: (lambda r: r[0] / r[1] if r[1] else None)(g.timing_get(i)) for nm, i in (("ed", 0), ("scan", 1), ("finish", 2), ("rng", 3))}
+if dist: dist.all_reduce(t, op=dist.ReduceOp.MAX)
+st = g.nb_stats()
+g.timing(True); g.timing_reset()
+sh.step(5, random_mode); g.sync()
+ph = {nm: round(g.timing_get(i)[0] / 5, 4) for nm, i in (("ed", 0), ("rng", 3), ("scan", 1), ("finish", 2))}
+g.timing(False)
+t0 = time.time(); sh.merge(); npairs2 = sh.build_pairlist(); g.sync(); t_rebuild = time.time() - t0
 if rank == 0:
-    halo = sh.halo_plan.recv_idx.size if sh.halo_plan is not None else None
-    print(f"n={n} world={world} mode={mode} scan_mode={scan_mode} random={random_mode} pairs={npairs} build={tb:.2f}s step={float(t):.3f} ms  kernels(ms/launch)={k} halo_rows={halo}", flush=True)
-if world > 1:
+    print(json.dumps(dict(n=n, world=world, kind=kind, laps=laps, gap=gap, qfac=qfac, random=random_mode, pairs=npairs,
+                          first_build_s=round(tb, 3), merge_rebuild_ms=round(t_rebuild * 1e3, 2), ms_per_step=round(float(t), 4),
+                          host_enqueue_ms=round(t_host / steps * 1e3, 4), phases_rank0=ph, **st)), flush=True)
+sh.close()
+if dist:
     dist.barrier(); dist.destroy_process_group()
