@@ -105,6 +105,12 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
 /* coordinates + velocities host -> device / device -> host (MPI_Crds, mpilib.cpp:106-130) */
 int edmd_set_state(edmd_engine* e, const edmd_tetrad* tets, int n);
 int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n);
+/* The same for this engine's owned tetrads only (edmd_set_shard): what one rank of a multi-GPU run moves per
+ * step.  Needs the coordinates (velocities) of all tetrads in one host block each (edmd_alloc_pinned).
+ * edmd_set_state_owned is asynchronous (stream-ordered before the next step), edmd_get_state_owned returns
+ * when the owned block of the host arrays is current. */
+int edmd_set_state_owned(edmd_engine* e, const edmd_tetrad* tets, int n);
+int edmd_get_state_owned(edmd_engine* e, edmd_tetrad* tets, int n);
 /* Fills ED_Forces[3N+1], random_Terms[3N], NB_Forces[3N+2] and temperature exactly as the
  * reference lays them out (MPI_ED_Forces, mpilib.cpp:74-94; master.cpp:308,316-317). */
 int edmd_get_forces(edmd_engine* e, edmd_tetrad* tets, int n);
@@ -267,7 +273,8 @@ int edmd_mark(edmd_engine* e, int slot);
 int edmd_mark_elapsed(edmd_engine* e, int slot_a, int slot_b, double* ms);
 /* Accumulated device time (ms) and launch count per kernel since the last reset, measured
  * with CUDA events on the engine stream.  which: 0 ED, 1 NB scan, 2 NB accumulate+clip,
- * 3 random, 4 merge, 5 pair list, 6 integrate, 7 layout (pack/unpack at the boundary). */
+ * 3 random, 4 merge, 5 pair list, 6 integrate, 7 layout (pack/unpack at the boundary), 8 the superposition
+ * kernel alone (part of 0). */
 int edmd_timing_enable(edmd_engine* e, int on);
 int edmd_timing_get(edmd_engine* e, int which, double* total_ms, long long* launches);
 int edmd_timing_reset(edmd_engine* e);

@@ -677,14 +677,19 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
     }
 }
 
-cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
-                             double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                             bool use_warp_kernel, cudaStream_t st) {
+cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
+                             cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
     superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
-    cudaError_t err = cudaGetLastError();
-    if (err != cudaSuccess) return err;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
+                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
+                              bool use_warp_kernel, cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    cudaError_t err;
     if (use_warp_kernel && ps.NEV <= kNevReg) {
         const size_t smem = sizeof(double) * (kNevReg * 3 + 3) * ps.S;
         // the opt-in to > 48 KB of dynamic shared memory is per device: remember which devices have it

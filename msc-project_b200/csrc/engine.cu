@@ -40,7 +40,7 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                              \
     } while (0)
 
-enum TimerId { T_ED = 0, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT, T_COUNT };
+enum TimerId { T_ED = 0, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT, T_SUP, T_COUNT };
 
 struct Timer {
     std::vector<cudaEvent_t> ev;   // start/stop pairs not yet folded
@@ -404,8 +404,11 @@ int do_ed(edmd_engine* e) {
     // The warp-per-tetrad projection stages a parameter set in shared memory once per run of tetrads that
     // share it: worth it when sets are shared (replicated DNA), not when every tetrad has its own.
     const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && (long long)e->n >= 8LL * e->P);
-    CK(launch_ed_forces(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
-                        e->t1 - e->t0, e->sp.scaled, warp, e->st));
+    timer_begin(e, T_SUP);
+    CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->st));
+    timer_end(e, T_SUP, 0);
+    CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
+                         e->t1 - e->t0, e->sp.scaled, warp, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -873,6 +876,56 @@ int edmd_get_state(edmd_engine* e, edmd_tetrad* tets, int n) {
                    e->h_stage + (size_t)which * e->total3 + e->off3_h[t], sizeof(double) * 3 * e->natoms_h[t]);
     }
     return 0;
+}
+
+// The owned tetrads [t0,t1) only: what one rank of a multi-process run moves per step when every rank keeps
+// its own block of the host Tetrad array current (the reference's workers received everything from the
+// master, master.cpp:279; with owner-computes each rank needs only its block).  Dense host fields required.
+int edmd_set_state_owned(edmd_engine* e, const edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_set_state_owned: n mismatch");
+    if (!dense_field(e, tets, 0) || !dense_field(e, tets, 1))
+        return fail(EDMD_ERR_ARG, "edmd_set_state_owned needs the coordinates (velocities) of all tetrads in one block each");
+    CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
+    if (int rc = snap_fence(e)) return rc;
+    const int cnt = e->t1 - e->t0;
+    if (cnt <= 0) return 0;
+    const long long o0 = e->off3_h[e->t0], o1 = e->off3_h[e->t1];
+    for (int which = 0; which < 2; which++) {
+        double* d = e->d_stage + (size_t)which * e->total3;
+        const double* h = which ? tets[0].velocities : tets[0].coordinates;
+        CK(cudaMemcpyAsync(d + o0, h + o0, sizeof(double) * (o1 - o0), cudaMemcpyHostToDevice, e->st));
+        CK(launch_pack_planes(d, e->d_off3 + e->t0, e->d_natoms + e->t0, (which ? e->vel : e->crd) + (size_t)e->t0 * 3 * e->S,
+                              cnt, e->S, e->st));
+        e->launches++;
+    }
+    e->hits_valid = false;
+    return 0;
+}
+
+int edmd_get_state_owned(edmd_engine* e, edmd_tetrad* tets, int n) {
+    if (int rc = check_ready(e, false)) return rc;
+    if (!tets || n != e->n) return fail(EDMD_ERR_ARG, "edmd_get_state_owned: n mismatch");
+    if (!dense_field(e, tets, 0) || !dense_field(e, tets, 1))
+        return fail(EDMD_ERR_ARG, "edmd_get_state_owned needs the coordinates (velocities) of all tetrads in one block each");
+    CK(cudaSetDevice(e->device));
+    if (int rc = normalize(e)) return rc;
+    if (int rc = snap_fence(e)) return rc;
+    const int cnt = e->t1 - e->t0;
+    if (cnt > 0) {
+        const long long o0 = e->off3_h[e->t0], o1 = e->off3_h[e->t1];
+        for (int which = 0; which < 2; which++) {
+            double* d = e->d_stage + (size_t)which * e->total3;
+            double* h = which ? tets[0].velocities : tets[0].coordinates;
+            CK(launch_unpack_planes((which ? e->vel : e->crd) + (size_t)e->t0 * 3 * e->S, e->d_off3 + e->t0, e->d_natoms + e->t0,
+                                    d, cnt, e->S, e->st));
+            e->launches++;
+            CK(cudaMemcpyAsync(h + o0, d + o0, sizeof(double) * (o1 - o0), cudaMemcpyDeviceToHost, e->st));
+        }
+    }
+    CK(cudaStreamSynchronize(e->st));
+    return peer_check(e);
 }
 
 int edmd_set_state_flat(edmd_engine* e, const double* crd, const double* vel) {

@@ -14,9 +14,11 @@ inline double nb_effective_cut2(const SimParams& sp) {
 }
 
 constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scratch (ed.cu)
-cudaError_t launch_ed_forces(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
-                             double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                             bool use_warp_kernel, cudaStream_t st);
+cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
+                             cudaStream_t st);
+cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
+                              double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
+                              bool use_warp_kernel, cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                            long long p0, long long p1, int S, double cut2_eff, int mode, int sms,

@@ -77,6 +77,8 @@ def load_library():
         "edmd_upload_tetrads": (C.c_int, [E, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
         "edmd_set_state": (C.c_int, [E, C.c_void_p, C.c_int]),
         "edmd_get_state": (C.c_int, [E, C.c_void_p, C.c_int]),
+        "edmd_set_state_owned": (C.c_int, [E, C.c_void_p, C.c_int]),
+        "edmd_get_state_owned": (C.c_int, [E, C.c_void_p, C.c_int]),
         "edmd_get_forces": (C.c_int, [E, C.c_void_p, C.c_int]),
         "edmd_set_forces": (C.c_int, [E, C.c_void_p, C.c_int]),
         "edmd_set_state_flat": (C.c_int, [E, PD, PD]),
@@ -247,7 +249,7 @@ class Engine:
     """One engine = one GPU.  Mirrors the reference call surface: the five EDMD methods
     (edmd.hpp:54-170) batched over tetrads, plus the Master bookkeeping on the hot path."""
 
-    T_ED, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT = range(8)
+    T_ED, T_SCAN, T_ACC, T_RNG, T_MERGE, T_PAIRS, T_INT, T_LAYOUT, T_SUP = range(9)
     BUF_CRD, BUF_VEL, BUF_FED, BUF_RND, BUF_FNB, BUF_HIT, BUF_CENTROID = range(7)
 
     def __init__(self, sys: EdmdSystem, device: int = 0, pinned: bool = True):
@@ -296,6 +298,15 @@ class Engine:
     def push_state(self):
         """Host Tetrad arrays (self.block.crd / .vel, edited in place) -> device."""
         self._ck(self.lib.edmd_set_state(self.h, self.block.ptr, self.sys.n))
+
+    def push_state_owned(self):
+        """Owned tetrads of the host Tetrad arrays -> device (asynchronous)."""
+        self._ck(self.lib.edmd_set_state_owned(self.h, self.block.ptr, self.sys.n))
+
+    def get_state_owned(self):
+        """Device -> the owned tetrads' part of the host Tetrad arrays (blocks until it is there)."""
+        self._ck(self.lib.edmd_get_state_owned(self.h, self.block.ptr, self.sys.n))
+        return self.block.crd, self.block.vel
 
     def get_forces(self):
         """dict(ed, ed_energy, rnd, nb, nb_energy[n,2], temperature) via the Tetrad structs."""
