@@ -1,19 +1,24 @@
 #!/usr/bin/env python
 """bench.py — EDMD hot-path throughput on B200 (contract: see the task statement).
 
-Workload (BASELINE.json configs[1], "C1"): synthetic 1,000-tetrad replicated GC DNA ring,
-all-pairs NB (mole_Cutoff = 1e9 -> 494,500 tetrad pairs = 3.14e10 atom pairs per step), random
-forces off.  A "step" = one pass of the hot path: ED forces -> NB tetrad-pair forces (+clip) ->
-velocity + coordinate update.  Metric: tetrad-pair interactions per second (steps/s alongside).
+Workload (BASELINE.json configs[3], "C3" — the configuration the metric quotes at 1/2/4/8 B200): synthetic
+100,000-tetrad replicated GC DNA ring, cutoff pair list (mole_Cutoff 30 A, cell-list builder), Langevin
+random forces ON with the reference's rand() stream.  A "step" = one pass of the hot path:
+ED forces -> random terms -> NB tetrad-pair forces (+clip) -> velocity + coordinate update.
+Metric: tetrad-pair interactions per second (steps/s alongside).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N > 1: launched by torchrun, one rank per GPU; the SAME workload is sharded (strong scaling):
-tetrads and the pair list are split into contiguous blocks, coordinates and hit flags are
-all-gathered over NCCL each step (msc-project_b200/dist.py).
+N > 1: launched by torchrun, one rank per GPU; the SAME workload is sharded (strong scaling): every rank owns a
+contiguous block of tetrads and a slice of the pair list; the per-step exchanges (halo pull, mask broadcast,
+barriers) are kernels inside the engine's CUDA graph over NVLink peer memory (msc-project_b200/csrc/peer.cu).
 
---impl reference: the reference's own CPU implementation of the path (oracle/_ref — the
-unmodified reference sources compiled here — else the plain-C port), all host threads, rank 0.
+--impl reference: the reference's own CPU implementation of the path (oracle/_ref — the unmodified reference
+sources compiled here — else the plain-C port) on all host threads, rank 0, on a bounded sample of C3.
+
+Extras beside the headline (N = 1): C1 (configs[1]: 1,000 tetrads, all-pairs list, random off — round 1's
+headline) with the brute-force FP64 distance kernel's roofline, and a contact-bearing coil (10,000 tetrads,
+~15 % of them in steric contact) with and without electrostatics, where the exact NB force kernel is timed.
 """
 import argparse
 import importlib
@@ -28,12 +33,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_TETRADS = 1000
+N_C3 = 100000
 ATOMS = 252
 FLOP_PER_ATOM_PAIR = 9          # 3 SUB + 3 MUL + 2 ADD + 1 MAX per atom pair
 METRIC = "tetrad_pair_interactions_per_sec"
 UNIT = "tetrad-pairs/s"
-WORKLOAD = "C1: synthetic 1000-tetrad replicated GC DNA ring, all-pairs NB (mole_Cutoff=1e9, 494500 tetrad pairs), random forces off"
+WORKLOAD = ("C3: synthetic 100000-tetrad replicated GC DNA ring, cutoff pair list (mole_Cutoff 30 A, cell-list "
+            "builder), Langevin random forces on (reference rand() stream)")
+RNG_TIME0 = 1000000000
+# real (de-duplicated) DRAM bytes per tetrad of the per-tetrad kernels, S = 256 atom slots, FP64:
+#   superpose: read crd (3*256*8) + write 24 doubles;  project: read crd + 24 doubles, write crd + fed + e_ed;
+#   random: write rnd;  finish: read vel, fed, rnd, crd, write vel, crd2 (parameter sets are L2-resident)
+PLANE = 3 * 256 * 8
+BYTES = {"superpose": PLANE + 192, "project": 3 * PLANE + 200, "random": PLANE, "finish": 6 * PLANE + 8}
 
 
 def load_pkg():
@@ -113,55 +125,77 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_reference(sys_obj, npairs_expected, budget_s, want_kind=None):
-    """Time the CPU implementation of the path on a bounded sample of the workload.
+def ring_pair_count(s):
+    """Length of the reference's pair list (master.cpp:180-210) for a planar ring, without building it.  Same
+    predicate in the same arithmetic (centroid summed sequentially in atom order, master.cpp:157-176; no FMA); only
+    chain neighbours — small |i-j| or |i-j| close to n across the ring closure — can be inside mole_Cutoff."""
+    import numpy as np
+    n = s.n
+    c = s.crd.reshape(n, ATOMS, 3)
+    cen = np.cumsum(c, axis=1)[:, -1, :] / ATOMS              # cumsum adds strictly left to right
+    cut2, least = float(s.params[5]) ** 2, float(s.params[7])
+    seps = sorted(set(range(1, 64)) | set(range(max(1, n - 63), n)))
+    total = 0
+    for sep in seps:
+        if not (sep > least and sep < n - least):
+            continue
+        d = cen[:n - sep] - cen[sep:]
+        r = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        total += int((r < cut2).sum())
+    return total
 
-    ED + integrate are timed on all tetrads (one pass, ~30 ms); NB on a contiguous sample of the
-    pair list sized for ~budget_s seconds with all host threads; the step time is assembled as
-    t_ed_int + t_nb_sample * (pairs / sample_pairs).  Returns dict(value, steps_per_s, ...)."""
+
+def config_dict(npairs):
+    """The workload description both arms print (identical dicts: the driver compares them)."""
+    return {"workload": WORKLOAD, "tetrads": N_C3, "tetrad_pairs": int(npairs), "atoms_per_tetrad": ATOMS,
+            "atom_pairs_per_step": int(npairs) * ATOMS * ATOMS, "random_forces": "on",
+            "inputs": "state planes 3.1 GB per GPU (> 126 MB L2): resident in HBM, nothing to flush between steps"}
+
+
+def cpu_sample(full, npairs_full, m, kind_wanted=None, reps=2):
+    """The reference CPU path on a bounded sample of C3: the first `m` tetrads of the ring (a chain segment with
+    its own cutoff pair list), all host threads.  Per-tetrad and per-pair costs are uniform along the ring, so the
+    full step is assembled as  t_tetrad_part * n/m + t_nb * pairs/pairs_sample.  The step is modelled the way the
+    reference's MPI run with W = cores workers executes it: ED and random terms in parallel worker blocks
+    (worker.cpp:155-162; measured on one thread and divided by W — libc rand() is per process there), NB in
+    parallel pair blocks (worker.cpp:166-179, measured on W threads), velocity/coordinate update serial on the
+    master (master.cpp:327-343)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    kind = want_kind or ("reference" if pyoracle.available("reference") else "port")
+    kind = kind_wanted or ("reference" if pyoracle.available("reference") else "port")
     if not pyoracle.available(kind):
         pyoracle.build(kind)
     cores = host_threads()
-    o = pyoracle.Oracle(sys_obj, kind)
-    npairs = o.build_pairs()
-    assert npairs == npairs_expected, (npairs, npairs_expected)
-    # calibration: 64 pairs per thread
-    cal = min(npairs, 64 * cores)
-    t_cal = o.time_nb(0, cal, cores)
-    rate = cal / t_cal
-    sample = int(min(npairs, max(cal, rate * budget_s * 0.25)))
-    t_nb = o.time_nb(0, sample, cores)
-    if t_nb < 0.5 * budget_s and sample < npairs:      # cold-start calibration under-estimates
-        sample = int(min(npairs, sample * 0.9 * budget_s / t_nb))
-        t_nb = o.time_nb(0, sample, cores)
-    # ED (threads) + integrate (serial on the master, master.cpp:327-343)
+    sub = full.subset(range(m))
+    o = pyoracle.Oracle(sub, kind)
+    o.set_time(RNG_TIME0)
+    np_sub = o.build_pairs()
+    t_nb = min(o.time_nb(0, np_sub, cores) for _ in range(reps))
     o.set_pairs([])
-    t0 = time.perf_counter()
-    o.forces(random_on=False, nthreads=cores)
-    o.update_velocities(); o.update_coordinates()
-    t_rest = time.perf_counter() - t0
-    step_s = t_rest + t_nb * (npairs / sample)
-    return {"value": npairs / step_s, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"NB: {sample} of {npairs} tetrad pairs in {t_nb:.2f} s on {cores} threads, scaled to the "
-                      f"full list; ED+integrate: all {sys_obj.n} tetrads once ({t_rest*1e3:.1f} ms)",
-            "steps_per_s": 1.0 / step_s}
+    t0 = time.perf_counter(); o.ed_forces(); t_ed = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.random_terms(); t_rng = time.perf_counter() - t0
+    t0 = time.perf_counter(); o.update_velocities(); o.update_coordinates(); t_int = time.perf_counter() - t0
+    scale_t, scale_p = full.n / m, npairs_full / np_sub
+    step_s = ((t_ed + t_rng) / cores + t_int) * scale_t + t_nb * scale_p
+    o.close()
+    return {"value": npairs_full / step_s, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {m} of {full.n} tetrads ({np_sub} of {npairs_full} tetrad pairs): NB {t_nb:.3f} s on {cores} threads; "
+                      f"ED {t_ed:.3f} s and random terms {t_rng:.3f} s measured on 1 thread and counted /{cores} (perfectly "
+                      f"parallel worker blocks, one libc stream per MPI worker); velocity+coordinate update {t_int:.3f} s serial "
+                      f"(master); scaled by tetrads and pairs",
+            "steps_per_s": 1.0 / step_s, "ms_per_step": step_s * 1e3}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     pkg = load_pkg()
-    s = pkg.make_ring(N_TETRADS, kind="ring", mole_cutoff=1e9)
-    npairs = N_TETRADS * (N_TETRADS - 1) // 2 - 5 * N_TETRADS
+    s = pkg.make_ring(N_C3, kind="ring")
+    npairs = ring_pair_count(s)
+    m = args.cpu_sample
     vals, last = [], None
-    per_step_budget = max(2.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
-    if args.ref_budget:
-        per_step_budget = args.ref_budget
     for it in range(args.warmup + args.steps):
-        r = cpu_reference(s, npairs, per_step_budget)
+        r = cpu_sample(s, npairs, m, reps=1)
         if it >= args.warmup:
             vals.append(r); last = r
     v = statistics.mean(x["value"] for x in vals)
@@ -169,7 +203,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / sps, "steps_per_sec": sps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "tetrads": N_TETRADS, "tetrad_pairs": npairs},
+            "data": "synthetic", "config": config_dict(npairs),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
                              "sample": last["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -177,16 +211,136 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------
+def phase_times(g, step_fn, reps):
+    """Per-phase device times (ms per step) from a short pass with the engine's CUDA-event timers on."""
+    g.timing(True); g.timing_reset()
+    step_fn(reps)
+    g.sync()
+    out = {}
+    for nm, idx in (("ed", g.T_ED), ("superpose", g.T_SUP), ("random", g.T_RNG), ("nb_distance", g.T_SCAN), ("finish", g.T_ACC)):
+        ms, _ = g.timing_get(idx)
+        out[nm] = ms / reps
+    out["project"] = out["ed"] - out["superpose"]
+    g.timing(False)
+    return out
+
+
+def timed_steps(g, step_fn, k, slot):
+    g.mark(slot); step_fn(k); g.mark(slot + 1)
+    return g.mark_elapsed(slot, slot + 1) / k
+
+
+def extra_c1(pkg, eng_mod, local, peak_tf):
+    """BASELINE configs[1]: 1,000 tetrads, all-pairs list (494,500 tetrad pairs), random off — the default step and
+    the brute-force distance kernels whose FP64 roofline SURVEY 8d defines."""
+    import torch
+    s = pkg.make_ring(1000, kind="ring", mole_cutoff=1e9)
+    g = pkg.Engine(s, device=local)
+    npairs = g.build_pairlist()
+    crd0, vel0 = s.crd.copy(), s.vel.copy()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
+    stream = torch.cuda.ExternalStream(g.stream, device=torch.device("cuda", local))
+    out = {"workload": "C1: synthetic 1000-tetrad replicated GC DNA ring, all-pairs NB (mole_Cutoff=1e9), random forces off",
+           "tetrads": 1000, "tetrad_pairs": npairs, "l2": "256 MB device fill between timed steps"}
+    flop = npairs * ATOMS * ATOMS * FLOP_PER_ATOM_PAIR
+    for key, mode in (("default_step", 4), ("full_scan", 1), ("fp32_prefilter", 2)):
+        g.set_nb_scan_mode(mode)
+        g.set_state(crd0, vel0)
+        g.step(3, 0)
+        k = 20 if mode == 4 else 5
+        tot = 0.0
+        for i in range(k):
+            g.mark(2 * i); g.step(1, 0); g.mark(2 * i + 1)
+            with torch.cuda.stream(stream):
+                flush.fill_(1)
+        g.sync()
+        ms = sum(g.mark_elapsed(2 * i, 2 * i + 1) for i in range(k)) / k
+        g.set_state(crd0, vel0)
+        ph = phase_times(g, lambda r: g.step(r, 0), 3)
+        ent = {"nb_scan_mode": mode, "ms_per_step": ms, "value": npairs / (ms * 1e-3), "unit": UNIT,
+               "nb_distance_ms": ph["nb_distance"]}
+        if mode in (1, 2):
+            ach = flop / (ph["nb_distance"] * 1e-3) / 1e12
+            ent.update({"bound": "fp64", "algorithmic_tflops": ach, "peak_tflops": peak_tf, "frac": ach / peak_tf,
+                        "hw_flop_frac": ach / peak_tf * 6.0 / 9.0 if mode == 1 else None,
+                        "note": "every one of the 63,504 atom pairs of every listed pair evaluated, like the reference; "
+                                "9 algorithmic flops per atom pair (SURVEY 8d) in 3 DFMA = 6 hardware flops (mode 1)"})
+        out[key] = ent
+    g.close()
+    return out
+
+
+def extra_contact(pkg, local, peak_tf):
+    """Contact-bearing workload: a two-lap coil of 10,000 tetrads whose laps touch over ~15 % of the chain, against
+    the clash-free ring of the same size; then the same with electrostatics on (qfac = 332.064/4, edmd.cpp:240),
+    where every atom pair inside atom_Cutoff goes through the exact force kernel."""
+    out = {"workload": "coil: 10000-tetrad two-lap closed coil (make_ring kind=coil, laps=2, lap_gap=40 A), cutoff pair list, random off"}
+    for name, kind, qfac in (("ring", "ring", 0.0), ("coil", "coil", 0.0), ("ring_qfac", "ring", 332.064 / 4.0),
+                             ("coil_qfac", "coil", 332.064 / 4.0)):
+        s = pkg.make_ring(10000, kind=kind, laps=2, lap_gap=40.0)
+        g = pkg.Engine(s, device=local)
+        g.set_nb_consts(100.0, qfac)
+        npairs = g.build_pairlist()
+        crd0, vel0 = s.crd.copy(), s.vel.copy()
+        g.step(3, 0); g.sync()
+        g.set_state(crd0, vel0)
+        ms = timed_steps(g, lambda r: g.step(r, 0), 20, 0)
+        st = g.nb_stats()
+        g.set_state(crd0, vel0)
+        ph = phase_times(g, lambda r: g.step(r, 0), 5)
+        ent = {"tetrad_pairs": npairs, "qfac": qfac, "ms_per_step": ms, "kernel_ms": ph, **st,
+               "marked_fraction": st["marked_tetrads"] / s.n}
+        # both owners evaluate a flagged pair's masked blocks: 2 x 1024 atom pairs per block
+        evals = 2 * 1024 * st["force_blocks"]
+        if evals:
+            ent["force_pass_atom_pair_evals"] = evals
+        out[name] = ent
+        g.close()
+    out["coil_over_ring"] = out["coil"]["ms_per_step"] / out["ring"]["ms_per_step"]
+    # the exact force kernel alone (qfac != 0): finish phase minus the streaming integrate of the same size
+    fin = out["coil_qfac"]["kernel_ms"]["finish"] - out["ring"]["kernel_ms"]["finish"]
+    ev = out["coil_qfac"].get("force_pass_atom_pair_evals", 0)
+    if fin > 0 and ev:
+        out["force_kernel_qfac"] = {"ms": fin, "atom_pair_evals_per_s": ev / (fin * 1e-3),
+                                    "note": "exact expression tree (no FMA, IEEE division), ~10 FP64 instructions per "
+                                            "evaluated atom pair + ~25 per pair inside atom_Cutoff; FP64-pipe activity from ncu "
+                                            "is in profiles/"}
+    return out
+
+
+def multi_gpu_parity(pkg, dmod, dist, torch, rank, world, local):
+    """Sharded engine vs one GPU, bit for bit, on a small contact-bearing system (outside the timed region)."""
+    import numpy as np
+    s = pkg.make_ring(200, kind="coil", laps=4, lap_gap=9.0)
+    g = pkg.Engine(s, device=local)
+    sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
+    sh.set_rng(RNG_TIME0, 1, 0)
+    npairs = sh.build_pairlist()
+    sh.step(5, 1); sh.merge(); sh.build_pairlist(); sh.step(3, 1); sh.finish()
+    c, v = g.get_state()
+    ok = True
+    if rank == 0:
+        g1 = pkg.Engine(s, device=local)
+        g1.set_rng(RNG_TIME0, 1, 0)
+        ok = g1.build_pairlist() == npairs
+        g1.step(5, 1); g1.merge(); g1.build_pairlist(); g1.step(3, 1)
+        c1, v1 = g1.get_state()
+        ok = ok and bool(np.array_equal(c, c1) and np.array_equal(v, v1))
+        g1.close()
+    sh.close(); g.close()
+    return ok
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline sampling (rank 0, N=1)")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="tetrads in the CPU baseline's sample of C3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ref-budget", type=float, default=0.0, help="--impl reference: seconds of CPU work per step (default: sized from --steps)")
-    ap.add_argument("--no-scale-config", action="store_true", help="skip the 100,000-tetrad (C3) measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C1 / contact-coil measurements beside the headline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -210,282 +364,160 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     warmup = max(args.warmup, 3)
-    s = pkg.make_ring(N_TETRADS, kind="ring", mole_cutoff=1e9)
+    steps = max(args.steps, 1)
+    s = pkg.make_ring(N_C3, kind="ring")
     g = pkg.Engine(s, device=local)
-    backend = dist_mod.EngineBackend(g, torch.device("cuda", local))
-    sh = dist_mod.ShardedEngine(backend, dist, s.n, rank, world)
+    sh = dist_mod.ShardedEngine(dist_mod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
+    sh.set_rng(RNG_TIME0, 1, 0); g.set_rng(RNG_TIME0, 1, 0)
     npairs = sh.build_pairlist()
-    g.set_nb_scan_mode(4)            # the engine default, stated: exact bounding-sphere culling on
-    crd0, vel0 = s.crd.copy(), s.vel.copy()
-
+    assert npairs == ring_pair_count(s), (npairs, ring_pair_count(s))
     peak_tf, _ = eng_mod.measure_fp64_peak(local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run_steps(k):
+        if world == 1:
+            g.step(k, 1)             # edmd_step: the public entry point (replays the captured step graph)
+        else:
+            sh.step(k, 1)            # the same call on every rank: the sharded step lives inside the engine
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()          # started early: nvidia-smi needs ~100 ms before its first sample
-    def one_step():
-        if world == 1:
-            g.step(1, 0)             # edmd_step: the public entry point (replays the captured step graph)
-        else:
-            sh.step(1, 0)            # sharded: kernels + NCCL / peer-memory exchanges (dist.py)
 
-    # The NB work after culling depends on the state, and the bench never merges the overlapping
-    # tetrads, so the state is put back to the initial one every RESET steps (the reference's ntsync
-    # block, config.txt:3) — outside the timed event pairs.
-    RESET = 100
-    g.set_state(crd0, vel0)          # host Tetrad block = initial state; g.push_state() re-uploads it
-
-    for _ in range(warmup):
-        one_step()
-        with backend.stream_ctx():
-            flush.fill_(1)
-    g.push_state()
+    run_steps(warmup)
     g.sync()
 
-    # ---- timed region: K steps, device time by CUDA events on the engine stream, L2 flushed
-    # (256 MB fill) between steps outside the event pairs ------------------------------------
+    # ---- timed region: K steps back to back, device time by CUDA events on the engine stream, max over ranks.
+    # The state (3.1 GB of planes per GPU) is far larger than the 126 MB L2, so nothing is flushed between steps.
     launches0 = g.launch_count
     barrier()
     sampler.mark_begin()
-    for k in range(args.steps):      # nothing in this loop blocks the host: the GPU queue stays full
-        if k and k % RESET == 0:
-            g.push_state()
-        g.mark(2 * k)
-        one_step()
-        g.mark(2 * k + 1)
-        with backend.stream_ctx():
-            flush.fill_(1)           # L2 flush, outside the (2k, 2k+1) event pair
+    g.mark(0); run_steps(steps); g.mark(1)
     barrier()
-    step_ms = [g.mark_elapsed(2 * k, 2 * k + 1) for k in range(args.steps)]
+    total_ms = max_over_ranks(g.mark_elapsed(0, 1))
     sampler.mark_end()
     launches = g.launch_count - launches0
-    total_ms = sum(step_ms)
-    if dist is not None:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-
-    # ---- per-phase breakdown: a separate short pass with the engine's per-phase CUDA-event timers on
-    # (the timers add event records between kernels, so they stay out of the timed region above)
-    kb = max(3, min(args.steps, 20))
-    g.push_state()
-    g.timing(True); g.timing_reset()
-    for _ in range(kb):
-        sh.step(1, 0)
-        with backend.stream_ctx():
-            flush.fill_(1)
-    barrier()
-    scan_ms, scan_n = g.timing_get(g.T_SCAN)
-    scan_phase_ms = scan_ms / kb                  # all launches of the distance pass in one step
-    kern = {}
-    for nm, idx in (("ed", g.T_ED), ("nb_scan", g.T_SCAN), ("nb_accumulate", g.T_ACC), ("integrate", g.T_INT)):
-        ms, k = g.timing_get(idx)
-        kern[nm] = ms / kb if k else None          # per STEP (a phase may be several launches)
-    g.timing(False)
-
-    # ---- informational variants of the NB distance pass (edmd_set_nb_scan_mode); every mode gives
-    # bit-identical forces (tests/test_gpu_edge.py).  full_scan is the brute-force kernel that evaluates
-    # all 63,504 atom pairs of every listed pair like the reference does: its FP64 roofline is reported
-    # in `roofline.full_scan`.
-    variants = {}
-    try:
-        for key, mode, what in (("full_scan", 1, "FP64 biased-Gram distance pass over ALL atom pairs of every listed pair (no culling)"),
-                                ("fp32_prefilter", 2, "FP32 packed-FFMA2 distance prefilter over all atom pairs + exact FP64 force path")):
-            g.set_nb_scan_mode(mode)
-            g.push_state()
-            sh.step(2, 0)
-            kv = max(3, min(args.steps, 10))
-            for k in range(kv):                      # step time: per-phase timers off
-                g.mark(60000 + 2 * k); sh.step(1, 0); g.mark(60001 + 2 * k)
-                with backend.stream_ctx():
-                    flush.fill_(1)
-            barrier()
-            v_ms = sum(g.mark_elapsed(60000 + 2 * k, 60001 + 2 * k) for k in range(kv)) / kv
-            g.timing(True); g.timing_reset()         # distance-pass time: a second, short pass with the timers on
-            for k in range(3):
-                sh.step(1, 0)
-                with backend.stream_ctx():
-                    flush.fill_(1)
-            barrier()
-            v_scan_ms, v_scan_n = g.timing_get(g.T_SCAN)
-            v_scan_ms /= 3.0
-            g.timing(False)
-            if dist is not None:
-                t = torch.tensor([v_ms], dtype=torch.float64, device=f"cuda:{local}")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                v_ms = float(t.item())
-            variants[key] = {"nb_scan_mode": mode, "what": what, "ms_per_step": v_ms,
-                             "nb_scan_ms": v_scan_ms if v_scan_n else None,
-                             "value": npairs / (v_ms * 1e-3), "unit": UNIT}
-    finally:
-        g.set_nb_scan_mode(4)
+    ms_per_step = total_ms / steps
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- e2e: through the C ABI with HOST buffers: set_state (H2D) -> step -> get_state (D2H)
-    e2e = None
+    # ---- per-phase breakdown (separate short pass: the timers put event records between the kernels)
+    ph = phase_times(g, lambda r: run_steps(r), 5)
+    barrier()
+    st = g.nb_stats()
+
+    # ---- the reference's outer loop (simulation.cpp:34-55): ntsync = 100 steps, merge, pair-list rebuild
+    barrier()
+    t0 = time.perf_counter()
+    run_steps(100); sh.merge(); sh.build_pairlist(); g.sync()
+    barrier()
+    block_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    # ---- e2e: through the C ABI with HOST buffers, one step per call.  One GPU: edmd_step_host on the caller's
+    # pinned Tetrad arrays (upload -> step -> download).  Several GPUs: every rank moves its OWN block of tetrads
+    # (edmd_set_state_owned / edmd_get_state_owned) around the same sharded step.
+    ke = max(3, min(steps, 10))
+    nbytes_all = 2 * s.crd.size * 8
     if world == 1:
-        # The host-side Tetrad structs (g.block: coordinates/velocities in pinned memory from
-        # edmd_alloc_pinned) are the caller's buffers: every step uploads them, runs the path and
-        # reads the new state back into them.
-        g.set_state(crd0, vel0)
-        for _ in range(3):
-            g.step_host(1, 0)
-        g.set_state(crd0, vel0)
-        ke = max(3, min(args.steps, 50))
+        for _ in range(2):
+            g.step_host(1, 1)
         t0 = time.perf_counter()
         for _ in range(ke):
-            # edmd_step_host: host Tetrad arrays -> device (H2D), one step, device -> host Tetrad arrays
-            # (D2H); returns when the new state is in the caller's (pinned) buffers
-            c1, v1 = g.step_host(1, 0)
+            g.step_host(1, 1)
         t_e2e = (time.perf_counter() - t0) / ke
-        nbytes = 2 * crd0.size * 8
-        e2e = {"value": npairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": t_e2e * 1e3}
     else:
-        # multi-rank end to end: rank-local state through host buffers every step
         sh.finish()
-        g.set_state(crd0, vel0)
-        ke = max(3, min(args.steps, 10))
+        g.get_state(copy=False)
+        for _ in range(2):
+            g.push_state_owned(); sh.step(1, 1); g.get_state_owned()
         barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
-            g.push_state()
-            sh.step(1, 0)
-            sh.finish()
-            c1, v1 = g.get_state(copy=False)
+            g.push_state_owned(); sh.step(1, 1); g.get_state_owned()
         barrier()
-        t_e2e = (time.perf_counter() - t0) / ke
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
-        nbytes = 2 * crd0.size * 8
-        e2e = {"value": npairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": t_e2e * 1e3}
+        t_e2e = max_over_ranks((time.perf_counter() - t0) / ke)
+    e2e = {"value": npairs / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes_all, "d2h_bytes_per_step": nbytes_all,
+           "ms_per_step": t_e2e * 1e3,
+           "how": ("edmd_step_host: host Tetrad arrays (pinned) -> device, one step, device -> host Tetrad arrays" if world == 1 else
+                   "per rank: edmd_set_state_owned (its block of the host arrays) -> sharded edmd_step -> edmd_get_state_owned; "
+                   "bytes are the total over ranks")}
 
-    # ---- the scaling configuration beside the headline: BASELINE configs[3] ("C3": 100,000 tetrads, cutoff
-    # pair list, Langevin random forces on), same N GPUs, halo-exchange sharding.  C1's culled step is ~0.15 ms,
-    # far too short to shard; this is the size the 8-GPU target is stated for.
-    c3 = None
-    if not args.no_scale_config:
-        g.close()
-        n3 = 100000
-        s3 = pkg.make_ring(n3, kind="ring")
-        g3 = pkg.Engine(s3, device=local)
-        sh3 = dist_mod.ShardedEngine(dist_mod.EngineBackend(g3, torch.device("cuda", local)), dist, s3.n, rank, world,
-                                     halo=True)
-        np3 = sh3.build_pairlist()
-        sh3.set_rng(1000000000, 1, 0); g3.set_rng(1000000000, 1, 0)
-        k3 = 20
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(pkg, dist_mod, dist, torch, rank, world, local)
+    owned = sh.plan.t1 - sh.plan.t0 if sh.plan is not None else s.n
+    sh.close()
+    g.close()
 
-        def c3_steps(k):
-            if world == 1:
-                g3.step(k, 1)
-            else:
-                sh3.step(k, 1)
-        c3_steps(3); g3.sync(); barrier()
-        g3.mark(0); c3_steps(k3); g3.mark(1)
-        barrier()
-        ms3 = g3.mark_elapsed(0, 1) / k3
-        if dist is not None:
-            t = torch.tensor([ms3], dtype=torch.float64, device=f"cuda:{local}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms3 = float(t.item())
-        # per-phase times (separate short pass, per-phase CUDA-event timers on) and the HBM roofline of the
-        # per-tetrad kernels: ALGORITHMIC bytes of SURVEY 8d (ED 96,872 B and integrate 48,384 B per tetrad,
-        # un-deduplicated parameters) / phase time, against MEASURED_PEAKS.json's copy bandwidth
-        g3.timing(True); g3.timing_reset()
-        kt = 3
-        sh3.step(kt, 1)
-        barrier()
-        ph = {}
-        for nm, idx in (("ed", g3.T_ED), ("nb_scan", g3.T_SCAN), ("nb_finish", g3.T_ACC), ("random", g3.T_RNG)):
-            ms, k = g3.timing_get(idx)
-            ph[nm] = ms / kt if k else None
-        g3.timing(False)
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras["c1"] = extra_c1(pkg, eng_mod, local, peak_tf)
+        extras["contact"] = extra_contact(pkg, local, peak_tf)
+
+    if rank == 0:
         try:
             hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); hbm_src = "MEASURED_PEAKS.json hbm_gbs"
         except Exception:
             hbm_peak = 6541.1; hbm_src = "fallback: the value MEASURED_PEAKS.json held when this was written"
-        owned = sh3.plan.t1 - sh3.plan.t0
-        hbm = {}
-        for nm, per in (("ed", 96872), ("nb_finish", 48384)):
+        # per-kernel roofline of the timed step (rank 0's share of the tetrads / pairs)
+        kernels = {}
+        for nm in ("superpose", "project", "random", "finish"):
             if ph.get(nm):
-                gbs = owned * per / (ph[nm] * 1e-3) / 1e9
-                hbm[nm] = {"algorithmic_bytes_per_tetrad": per, "achieved_GBs": gbs, "peak_GBs": hbm_peak, "frac": gbs / hbm_peak}
-        c3 = {"workload": "C3: synthetic 100,000-tetrad GC DNA ring, cutoff pair list (cell-list builder), Langevin "
-                          "random forces on (reference rand() stream)", "tetrads": n3, "tetrad_pairs": np3,
-              "n_gpus": world, "steps": k3, "ms_per_step": ms3, "steps_per_sec": 1e3 / ms3,
-              "value": np3 / (ms3 * 1e-3), "unit": UNIT, "scaling": "strong",
-              "state_bytes_resident": "inputs (>126 MB L2) resident in HBM, no flush needed",
-              "kernel_ms": ph,
-              "hbm_roofline": {**hbm, "peak_source": hbm_src,
-                               "note": "algorithmic bytes count each tetrad's own copy of its parameters (90.8 KB) as the "
-                                       "reference stores them; the engine de-duplicates parameter sets, so the real DRAM "
-                                       "traffic is ~4x smaller for ED and frac can exceed 1"}}
-        g3.close()
-
-    if rank == 0:
-        traffic = full_traffic = None
-        try:   # DRAM bytes per launch of the dominant kernels, from the committed ncu captures
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
-            if world == 1:
-                c = tj.get("nb_scan_cull_kernel"); f = tj.get("nb_scan_kernel<1>")
-                traffic = c["dram_bytes_read"] + c["dram_bytes_write"] if c else None
-                full_traffic = f["dram_bytes_read"] + f["dram_bytes_write"] if f else None
-        except Exception:
-            pass
-        ms_per_step = total_ms / args.steps
-        my_pairs = sh.plan.p1 - sh.plan.p0
-        flop_launch = my_pairs * ATOMS * ATOMS * FLOP_PER_ATOM_PAIR
-        achieved = flop_launch / (scan_phase_ms * 1e-3) / 1e12 if scan_n else None
-        fs = variants.get("full_scan") or {}
-        fs_ach = flop_launch / (fs["nb_scan_ms"] * 1e-3) / 1e12 if fs.get("nb_scan_ms") else None
+                gbs = owned * BYTES[nm] / (ph[nm] * 1e-3) / 1e9
+                kernels[nm] = {"ms": ph[nm], "bound": "hbm", "bytes_per_tetrad": BYTES[nm], "achieved": gbs, "peak": hbm_peak,
+                               "unit": "GB/s", "frac": gbs / hbm_peak}
+        if ph.get("nb_distance"):
+            # the culled distance pass evaluates only the 32 x 32 atom blocks the bounding spheres cannot exclude
+            ev = st.get("sphere_blocks", 0) * 1024
+            tf = ev * FLOP_PER_ATOM_PAIR / (ph["nb_distance"] * 1e-3) / 1e12
+            kernels["nb_distance"] = {"ms": ph["nb_distance"], "bound": "fp64", "evaluated_atom_pairs": ev,
+                                      "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                                      "note": "three launches (bounding spheres, pair selection, masked distance kernel); flops "
+                                              "counted for EVALUATED atom pairs only, 9 per pair"}
+        dom = max(kernels, key=lambda k: kernels[k]["ms"]) if kernels else None
+        roof = {"kernel": dom, **{k: v for k, v in (kernels.get(dom) or {}).items() if k != "ms"},
+                "ms_per_launch": (kernels.get(dom) or {}).get("ms"), "traffic": None,
+                "traffic_note": "not measured inside this run; ncu dram bytes per launch are in profiles/",
+                "peak_source": hbm_src + "; FP64: DFMA microbenchmark edmd_measure_fp64_peak, measured in this run",
+                "kernels": kernels}
+        if "c1" in extras and "full_scan" in extras["c1"]:
+            fs = extras["c1"]["full_scan"]
+            roof["nb_full_scan"] = {"kernel": "nb_scan_kernel<1> on C1 (every atom pair of every listed pair, like the reference)",
+                                    "bound": "fp64", "achieved": fs["algorithmic_tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": fs["frac"], "hw_flop_frac": fs["hw_flop_frac"], "ms_per_launch": fs["nb_distance_ms"]}
         line = {
             "metric": METRIC, "value": npairs / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "steps_per_sec": 1e3 / ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "tetrads": N_TETRADS, "tetrad_pairs": npairs,
-                       "atom_pairs_per_step": npairs * ATOMS * ATOMS,
-                       "nb_scan_mode": 4,
-                       "parallelism": f"tetrad-block x pair-slice sharding over {world} GPU(s)",
-                       "l2": "256 MB device fill between timed steps (outside the event pairs)",
-                       "state": f"restored to the initial state every {RESET} steps (outside the event pairs)",
-                       **({"note": "the culled C1 step takes ~0.11 ms on ONE GPU: sharding it over more GPUs cannot pay "
-                                   "(latency of the two exchanges per step); the multi-GPU configuration is scale_config "
-                                   "(C3, 100,000 tetrads)"} if world > 1 else {})},
+            "config": config_dict(npairs),
+            "parallelism": f"{world} GPU(s): contiguous tetrad blocks x equal pair slices; exchanges over NVLink peer memory "
+                           "inside the step graph" if world > 1 else "1 GPU",
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,
-            "kernel_ms": kern,
-            "variants": variants,
-            "scale_config": c3,
-            "roofline": {"kernel": "NB distance pass: group_bounds + pair_select + nb_scan_cull_kernel (engine default)",
-                         "bound": "fp64", "achieved": achieved,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": traffic,
-                         "note": "achieved counts the 9 ALGORITHMIC flops of edmd.cpp:251-256 for each of the 63,504 atom "
-                                 "pairs of every LISTED tetrad pair, as SURVEY 8d prescribes regardless of culling.  The "
-                                 "default pass proves most 32x32 atom blocks empty with bounding spheres and never "
-                                 "evaluates them, so frac >> 1 measures the work avoided, not pipe utilisation; the "
-                                 "kernel-quality figure is full_scan: the same pass with culling off (every atom pair "
-                                 "evaluated, 3 DFMA = 6 hardware flops each; hw_flop_frac = frac * 6/9)",
-                         "full_scan": {"kernel": "nb_scan_kernel<1> (biased Gram form, no culling)", "achieved": fs_ach,
-                                       "frac": (fs_ach / peak_tf) if fs_ach else None,
-                                       "hw_flop_frac": (fs_ach / peak_tf * 6.0 / 9.0) if fs_ach else None,
-                                       "ms_per_launch": fs.get("nb_scan_ms"), "traffic": full_traffic},
-                         "peak_source": "measured in this run: DFMA microbenchmark edmd_measure_fp64_peak "
-                                        "(MEASURED_PEAKS.json has no FP64 entry)",
-                         "algorithmic_flop_per_launch": flop_launch},
+            "kernel_ms": ph,
+            "nb_stats": st,
+            "ntsync_block": {"steps": 100, "ms_total_incl_merge_and_pairlist_rebuild": block_ms,
+                             "ms_per_step": block_ms / 100.0},
+            "roofline": roof,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
+        if extras:
+            line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(s, npairs, args.cpu_budget)
+            line["cpu_baseline"] = cpu_sample(s, npairs, args.cpu_sample)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

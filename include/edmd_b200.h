@@ -283,8 +283,9 @@ long long edmd_launch_count(edmd_engine* e);   /* kernels launched since create 
 int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs);
 /* More of the same: out = {tetrad pairs flagged, owned tetrads in at least one flagged pair, 32 x 32 atom
  * blocks the force pass evaluates (set bits of the per-pair block masks), tetrad pairs the bounding-sphere
- * tests of the culled distance pass let through (0 in the brute-force modes)}. */
-int edmd_nb_stats_ex(edmd_engine* e, long long out[4]);
+ * tests of the culled distance pass let through, 32 x 32 atom blocks the culled distance kernel evaluated
+ * (set bits of the sphere masks); the last two are 0 in the brute-force modes}. */
+int edmd_nb_stats_ex(edmd_engine* e, long long out[5]);
 
 /* FP64 peak of this device measured with a dependent-free DFMA loop (the roofline
  * denominator for the NB kernel; MEASURED_PEAKS.json has no FP64 entry). */

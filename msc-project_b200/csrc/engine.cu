@@ -83,6 +83,7 @@ struct edmd_engine {
     double *e_ed = nullptr, *e_nb = nullptr, *temp = nullptr, *cen = nullptr, *sup = nullptr;
     int* d_mark = nullptr;            // [2n+1] per-tetrad "in a flagged pair" flags, list counter, list of marked tetrads
     unsigned char* d_dirty = nullptr; // [n] fnb of this tetrad is non-zero from an earlier step
+    double* d_epart = nullptr;        // [n][8][2] pair energies per slot group (force pass -> finish kernel)
     double* d_gb = nullptr;                 // [n][8][4] group + [n][4] tetrad bounding spheres (scan mode 4)
     int* d_perm = nullptr;                  // [P][kMaxStride] slot -> atom, compact groups of 32 (culling scan, force pass)
     unsigned long long* d_grp = nullptr;    // [P][32] atom -> slot group, byte c of entry l = group of atom 32c+l
@@ -224,6 +225,7 @@ void free_system(edmd_engine* e) {
     e->snap_pending[0] = e->snap_pending[1] = false;
     cudaFree(e->d_calls); e->d_calls = nullptr;
     cudaFree(e->d_mark); cudaFree(e->d_dirty); e->d_mark = nullptr; e->d_dirty = nullptr;
+    cudaFree(e->d_epart); e->d_epart = nullptr;
     cudaFree(e->d_perm); e->d_perm = nullptr;
     cudaFree(e->d_grp); e->d_grp = nullptr;
     cudaFree(e->d_gb); cudaFree(e->d_pmask); e->d_gb = nullptr; e->d_pmask = nullptr; e->pmask_cap = 0;
@@ -445,9 +447,10 @@ int do_accumulate(edmd_engine* e) {
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)e->n, e->st));
     timer_begin(e, T_ACC);
     CK(launch_nb_accumulate(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_adj_off,
-                            e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->t0,
-                            e->t1 - e->t0, e->S, e->sp, e->nb_clip, e->st));
-    timer_end(e, T_ACC, 1);
+                            e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->d_epart,
+                            reinterpret_cast<unsigned*>(e->d_mark + e->n + 1), e->t0, e->t1 - e->t0, e->S, e->sms, e->sp,
+                            e->nb_clip, e->st));
+    timer_end(e, T_ACC, 2);
     return 0;
 }
 // accumulate + clip + velocity + coordinate update in one kernel (edmd_step, edmd_nb_finish)
@@ -460,10 +463,10 @@ int do_finish(edmd_engine* e) {
     } else {
         timer_begin(e, T_ACC);
         CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
-                                  e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->ps, e->vel,
-                                  e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty, e->n,
-                                  e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
-        timer_end(e, T_ACC, e->np > 0 ? 4 : 1);
+                                  e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->d_epart, e->ps,
+                                  e->vel, e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty,
+                                  e->n, e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
+        timer_end(e, T_ACC, e->np > 0 ? 3 : 1);
         e->latest_in_crd2 = true;
     }
     // Peer mode: the masks were stored by every rank's distance kernel; now that this rank has consumed them
@@ -765,7 +768,9 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->obs, 4 * (size_t)n));
     e->e_ed = e->obs; e->e_nb = e->obs + n; e->temp = e->obs + 3 * (size_t)n;
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
-    CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 2)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 4)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(dev_alloc(&e->d_epart, 16 * (size_t)n));
+    CK(cudaMemsetAsync(e->d_epart, 0, sizeof(double) * 16 * (size_t)n, e->st));
     CK(dev_alloc(&e->d_gb, (size_t)n * 36));
     CK(cudaMemsetAsync(e->d_dirty, 1, (size_t)n, e->st));   // unknown force contents: treat as dirty
     CK(dev_alloc(&e->sup, (size_t)kSupWordsHost * n));
@@ -1505,7 +1510,7 @@ int edmd_nb_stats(edmd_engine* e, long long* flagged_pairs) {
     return 0;
 }
 
-int edmd_nb_stats_ex(edmd_engine* e, long long out[4]) {
+int edmd_nb_stats_ex(edmd_engine* e, long long out[5]) {
     if (int rc = check_ready(e, true)) return rc;
     if (!out) return fail(EDMD_ERR_ARG, "null output");
     CK(cudaSetDevice(e->device));
@@ -1517,7 +1522,7 @@ int edmd_nb_stats_ex(edmd_engine* e, long long out[4]) {
         CK(cudaMemcpy(pr.data(), e->d_pairs, sizeof(int2) * (size_t)e->np, cudaMemcpyDeviceToHost));
     }
     std::vector<unsigned char> marked((size_t)e->n, 0);
-    out[0] = out[1] = out[2] = out[3] = 0;
+    out[0] = out[1] = out[2] = out[3] = out[4] = 0;
     for (long long p = 0; p < e->np; p++) {
         if (!h[p]) continue;
         out[0]++;
@@ -1529,6 +1534,10 @@ int edmd_nb_stats_ex(edmd_engine* e, long long out[4]) {
         unsigned cnt = 0;
         CK(cudaMemcpy(&cnt, e->d_pmask, sizeof(unsigned), cudaMemcpyDeviceToHost));
         out[3] = cnt;
+        // work items {pair index, sphere mask} follow the 16-byte counter slot (nb.cu: CullItem)
+        std::vector<unsigned long long> items(2 * (size_t)cnt);
+        if (cnt) CK(cudaMemcpy(items.data(), e->d_pmask + 2, sizeof(unsigned long long) * items.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; i++) out[4] += __builtin_popcountll(items[2 * i + 1]);
     }
     return 0;
 }

@@ -31,17 +31,19 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
 cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
 // hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the
-// per-parameter-set slot -> atom and atom -> slot-group tables the masks refer to (engine.cu)
+// per-parameter-set slot -> atom and atom -> slot-group tables the masks refer to (engine.cu); epart: [n][8][2]
+// per-slot-group pair energies; ticket: work-item counter
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned long long* hit, const long long* adj_off, const int* adj_partner,
                                  const int* adj_pair, const int* perm, const unsigned long long* grp, double* fnb,
-                                 double* e_nb, int t0, int count, int S, const SimParams& sp, int clip, cudaStream_t st);
+                                 double* e_nb, double* epart, unsigned* ticket, int t0, int count, int S, int sms,
+                                 const SimParams& sp, int clip, cudaStream_t st);
 
-// mark: int [2n + 1] scratch (flags, list counter, compact list of marked tetrads)
+// mark: int [2n + 2] scratch (flags, list counter, work-item counter, compact list of marked tetrads)
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
                                    const unsigned long long* hit, const int2* pairs, long long np, const long long* adj_off,
                                    const int* adj_partner, const int* adj_pair, const int* perm,
-                                   const unsigned long long* grp, double* fnb, double* e_nb,
+                                   const unsigned long long* grp, double* fnb, double* e_nb, double* epart,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
                                    const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
                                    int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st);

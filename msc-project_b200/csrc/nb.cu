@@ -28,6 +28,8 @@
 // With qfac = 0 (the reference's hard-coded value) an atom pair changes the result only if
 // r^2 < 2 (a = max(0, 2 - r^2) > 0): in-cutoff pairs with a = 0 add +-0.0.  The effective cutoff
 // is therefore min(atom_Cutoff^2, 2.0) when qfac == 0 and atom_Cutoff^2 otherwise.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "step_math.cuh"
@@ -668,22 +670,24 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 // ---------------------------------------------------------------------------------------------
 // Exact force pass (edmd.cpp:258-276, worker.cpp:166-179, master.cpp:297-322).
 //
-// One CTA per tetrad that takes part in a flagged pair; warp w owns slot group w of the tetrad (the
-// spatially compact group of <= 32 atoms the scan's block masks refer to), lane l the atom in slot
-// 32w + l.  The eight warps walk the tetrad's partners independently (no CTA barrier inside the walk):
-//   * 32 adjacency entries at a time, each lane fetches one entry's block mask and reduces it to the
-//     8-bit set of PARTNER groups that can reach this warp's group; entries with an empty set are
-//     skipped by a ballot — for the typical contact only one or two warps of the CTA have work;
-//   * for a kept partner the warp gathers the atoms of those partner groups in ASCENDING ATOM ORDER
-//     (per-set table atom -> group) into its own shared-memory strip, then every lane runs the
-//     reference's expression tree against each gathered atom.
-// Bit-exactness: a lane adds its atom's contributions in ascending partner-atom order starting from
-// +0.0 per pair, then adds the pair partial to the tetrad total in pair-list order — the reference's
-// order.  Skipped atom pairs lie outside the effective cutoff and would add +-0.0, which never
-// changes a sum that started at +0.0.  d = x(t1) - x(t2) and the sign of the update depend on which
-// end of the pair this tetrad is, but  F1_i -= d * pf  and  F2_j += d * pf  are both, exactly,
-// "mine += (x_partner - x_mine) * pf" (negation commutes with IEEE rounding), so one form serves.
+// Work item = (marked tetrad, slot group): ONE WARP owns slot group w of a tetrad that takes part in a flagged
+// pair — the spatially compact group of <= 32 atoms the scan's block masks refer to — lane l the atom in slot
+// 32w + l.  Items are handed out through an atomic counter, so the warps of the whole GPU stay busy however
+// unevenly the contacts are spread (most groups of a marked tetrad touch nothing and cost one adjacency walk).
+//   * 32 adjacency entries at a time, each lane fetches one entry's block mask and reduces it to the 8-bit set
+//     of PARTNER groups that can reach this warp's group; entries with an empty set are skipped by a ballot;
+//   * for a kept partner the warp gathers the atoms of those partner groups in ASCENDING ATOM ORDER (per-set
+//     table atom -> group) into its own shared-memory strip, then every lane runs the reference's expression
+//     tree against each gathered atom.
+// Bit-exactness: a lane adds its atom's contributions in ascending partner-atom order starting from +0.0 per
+// pair, then adds the pair partial to the tetrad total in pair-list order — the reference's order.  Skipped
+// atom pairs lie outside the effective cutoff and would add +-0.0, which never changes a sum that started at
+// +0.0.  d = x(t1) - x(t2) and the sign of the update depend on which end of the pair this tetrad is, but
+// F1_i -= d * pf  and  F2_j += d * pf  are both, exactly, "mine += (x_partner - x_mine) * pf" (negation commutes
+// with IEEE rounding), so one form serves.  Each atom's force is produced by exactly one lane in a fixed
+// order: no atomics on forces, bit-stable, and bit-identical to the W = 1 reference.
 constexpr int kAccBuf = 128;    // gathered partner atoms per round (4 chunks of 32)
+constexpr int kForceWarps = 4;  // warps per CTA of the force kernel (independent of each other)
 
 struct AccArgs {
     const double* crd;         // [n][3][S]
@@ -697,18 +701,19 @@ struct AccArgs {
     const int* perm;           // [P][kMaxStride] slot -> atom (-1 = empty slot)
     const unsigned long long* grp;   // [P][32]: byte c of entry l = slot group of atom 32c + l (0xff = no atom)
     double* fnb;               // [n][3][S] out, clipped
-    double* e_nb;              // [n][2] out: NB energy, electrostatic energy (unclipped)
-    int t0;
+    double* epart;             // [n][8][2] out: per slot group, NB energy and electrostatic energy (unclipped)
+    const int* list;           // compact list of tetrads to process, or nullptr: tetrads t0 .. t0+count-1
+    const unsigned* count;     // device-side length of `list` (nullptr: `count_host`)
+    unsigned* ticket;          // work-item counter (zeroed before the launch)
+    int t0, count_host;
     int S;
     double cut2_eff;           // see file header
     double krep, qfac;
     int clip;                  // 1: clamp force components to [-1,1] (master.cpp:304-305)
 };
 
-struct AccSmem {
-    double px[kWarps][kAccBuf], py[kWarps][kAccBuf], pz[kWarps][kAccBuf], pq[kWarps][kAccBuf];
-    double f[3][kMaxStride];   // clipped force by ATOM index (hand-over to the integrate half)
-    double red[2][kWarps];
+struct ForceSmem {
+    double px[kForceWarps][kAccBuf], py[kForceWarps][kAccBuf], pz[kForceWarps][kAccBuf], pq[kForceWarps][kAccBuf];
 };
 
 // bits g of the result = bits 8g + r of m, g = 0..7 (one multiply gathers the eight strided bits:
@@ -718,7 +723,7 @@ __device__ __forceinline__ unsigned column_bits(unsigned long long m, int r) {
 }
 
 template <bool HAS_Q>
-__device__ __forceinline__ void acc_partner(const AccArgs& A, AccSmem& sm, int w, int lane, int u, unsigned pm,
+__device__ __forceinline__ void acc_partner(const AccArgs& A, ForceSmem& sm, int w, int lane, int u, unsigned pm,
                                             double xi, double yi, double zi, double qi,
                                             double& F0, double& F1, double& F2, double& E0, double& E1) {
     const unsigned full = 0xffffffffu;
@@ -774,101 +779,117 @@ __device__ __forceinline__ void acc_partner(const AccArgs& A, AccSmem& sm, int w
     E0 += pe0; E1 += pe1;
 }
 
-// Accumulates, clips and stores the NB force of tetrad t; leaves the clipped force of ATOM threadIdx.x
-// in f[] (the integrate half maps thread <-> atom).
 template <bool HAS_Q>
-__device__ __forceinline__ void nb_accumulate_tetrad(const AccArgs& A, int t, AccSmem& sm, double f[3]) {
+__global__ void __launch_bounds__(32 * kForceWarps, 5) nb_force_kernel(AccArgs A) {
+    __shared__ ForceSmem sm;
     const unsigned full = 0xffffffffu;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     const int S = A.S;
-    const int ps = A.param_id[t];
-    const int na = A.natoms[t];
-    const int a = A.perm[(size_t)ps * kMaxStride + tid];     // my atom (slot order: warp w = group w)
-    const bool on = a >= 0;
-    const double* X = A.crd + (size_t)t * 3 * S;
-    // an empty slot sits far away from everything: it never passes the cutoff test
-    double xi = 1e150, yi = 1e150, zi = 1e150, qi = 0.0;
-    if (on) {
-        xi = X[a]; yi = X[S + a]; zi = X[2 * S + a];
-        if (HAS_Q) qi = A.chg[(size_t)ps * S + a];
-    }
-    double F0 = 0.0, F1 = 0.0, F2 = 0.0;   // tetrad totals, pair-list order
-    double E0 = 0.0, E1 = 0.0;             // this lane's share of the pair energies
+    const unsigned items = 8u * (A.count ? *A.count : (unsigned)A.count_host);
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(A.ticket, 1u);
+        item = __shfl_sync(full, item, 0);
+        if (item >= items) return;
+        const int t = A.list ? A.list[item >> 3] : A.t0 + (int)(item >> 3);
+        const int w = (int)(item & 7u);                          // my slot group
+        const int ps = A.param_id[t];
+        const int a = A.perm[(size_t)ps * kMaxStride + 32 * w + lane];   // my atom
+        const bool on = a >= 0;
+        const double* X = A.crd + (size_t)t * 3 * S;
+        // an empty slot sits far away from everything: it never passes the cutoff test
+        double xi = 1e150, yi = 1e150, zi = 1e150, qi = 0.0;
+        if (on) {
+            xi = X[a]; yi = X[S + a]; zi = X[2 * S + a];
+            if (HAS_Q) qi = A.chg[(size_t)ps * S + a];
+        }
+        double F0 = 0.0, F1 = 0.0, F2 = 0.0;   // tetrad totals, pair-list order
+        double E0 = 0.0, E1 = 0.0;             // this lane's share of the pair energies
 
-    const long long e_begin = A.adj_off[t], e_end = A.adj_off[t + 1];
-    for (long long base = e_begin; base < e_end; base += 32) {
-        const long long e = base + lane;
-        unsigned pmv = 0; int code = 0;
-        if (e < e_end) {
-            const unsigned long long m = A.hit[A.adj_pair[e]];
-            if (m) {
-                code = A.adj_partner[e];
-                const int u = code & 0x7fffffff;
-                // mask bit 8g + r: group r of the lower-numbered tetrad x group g of the higher-numbered one
-                pmv = t < u ? column_bits(m, w) : (unsigned)(m >> (8 * w)) & 0xffu;
+        const long long e_begin = A.adj_off[t], e_end = A.adj_off[t + 1];
+        for (long long base = e_begin; base < e_end; base += 32) {
+            const long long e = base + lane;
+            unsigned pmv = 0; int code = 0;
+            if (e < e_end) {
+                const unsigned long long m = A.hit[A.adj_pair[e]];
+                if (m) {
+                    code = A.adj_partner[e];
+                    const int u = code & 0x7fffffff;
+                    // mask bit 8g + r: group r of the lower-numbered tetrad x group g of the higher-numbered one
+                    pmv = t < u ? column_bits(m, w) : (unsigned)(m >> (8 * w)) & 0xffu;
+                }
+            }
+            unsigned todo = __ballot_sync(full, pmv != 0u);
+            while (todo) {
+                const int b = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int u = __shfl_sync(full, code, b) & 0x7fffffff;
+                const unsigned pm = __shfl_sync(full, pmv, b);
+                acc_partner<HAS_Q>(A, sm, wslot, lane, u, pm, xi, yi, zi, qi, F0, F1, F2, E0, E1);
             }
         }
-        unsigned todo = __ballot_sync(full, pmv != 0u);
-        while (todo) {
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int u = __shfl_sync(full, code, b) & 0x7fffffff;
-            const unsigned pm = __shfl_sync(full, pmv, b);
-            acc_partner<HAS_Q>(A, sm, w, lane, u, pm, xi, yi, zi, qi, F0, F1, F2, E0, E1);
+
+        // clip (master.cpp:304-305) and store
+        if (A.clip) {
+            F0 = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
+            F1 = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
+            F2 = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
         }
+        double* F = A.fnb + (size_t)t * 3 * S;
+        if (on) { F[a] = F0; F[S + a] = F1; F[2 * S + a] = F2; }
+        // this group's share of the tetrad's pair energies: fixed-order butterfly, summed over the groups later
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { E0 += __shfl_xor_sync(full, E0, o); E1 += __shfl_xor_sync(full, E1, o); }
+        if (lane == 0) { A.epart[((size_t)t * 8 + w) * 2] = E0; A.epart[((size_t)t * 8 + w) * 2 + 1] = E1; }
     }
-
-    // clip (master.cpp:304-305) and store
-    double c0 = F0, c1 = F1, c2 = F2;
-    if (A.clip) {
-        c0 = F0 < -1.0 ? -1.0 : (F0 > 1.0 ? 1.0 : F0);
-        c1 = F1 < -1.0 ? -1.0 : (F1 > 1.0 ? 1.0 : F1);
-        c2 = F2 < -1.0 ? -1.0 : (F2 > 1.0 ? 1.0 : F2);
-    }
-    double* F = A.fnb + (size_t)t * 3 * S;
-    if (on) {
-        F[a] = c0; F[S + a] = c1; F[2 * S + a] = c2;
-        sm.f[0][a] = c0; sm.f[1][a] = c1; sm.f[2][a] = c2;
-    }
-    double ev[2] = {E0, E1};
-    block_sum<2>(ev, sm.red);              // (also the barrier that publishes sm.f)
-    if (tid == 0) { A.e_nb[2 * (size_t)t] = ev[0]; A.e_nb[2 * (size_t)t + 1] = ev[1]; }
-    f[0] = f[1] = f[2] = 0.0;
-    if (tid < na) { f[0] = sm.f[0][tid]; f[1] = sm.f[1][tid]; f[2] = sm.f[2][tid]; }
-    __syncthreads();                       // sm.f is rewritten by this CTA's next tetrad
 }
 
-template <bool HAS_Q>
-__global__ void __launch_bounds__(kThreads, 2) nb_accumulate_kernel(AccArgs A) {
-    __shared__ AccSmem sm;
-    double f[3];
-    nb_accumulate_tetrad<HAS_Q>(A, A.t0 + blockIdx.x, sm, f);
+// e_nb[t] = sum over the eight slot groups, in group order (one thread per tetrad)
+__global__ void nb_energy_kernel(const double* epart, double* e_nb, int t0, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const size_t t = (size_t)(t0 + i);
+    double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { e0 += epart[(t * 8 + w) * 2]; e1 += epart[(t * 8 + w) * 2 + 1]; }
+    e_nb[2 * t] = e0; e_nb[2 * t + 1] = e1;
 }
 
+static void launch_force(const AccArgs& A, int grid, cudaStream_t st) {
+    if (A.qfac != 0.0) nb_force_kernel<true><<<grid, 32 * kForceWarps, 0, st>>>(A);
+    else               nb_force_kernel<false><<<grid, 32 * kForceWarps, 0, st>>>(A);
+}
+
+// Unfused form (edmd_nb_accumulate / edmd_nb_forces): every owned tetrad is a work item.
 cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int* param_id, const double* chg,
                                  const unsigned long long* hit, const long long* adj_off, const int* adj_partner,
                                  const int* adj_pair, const int* perm, const unsigned long long* grp, double* fnb,
-                                 double* e_nb, int t0, int count, int S, const SimParams& sp, int clip, cudaStream_t st) {
+                                 double* e_nb, double* epart, unsigned* ticket, int t0, int count, int S, int sms,
+                                 const SimParams& sp, int clip, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, e_nb, t0, S,
-              nb_effective_cut2(sp), sp.krep, sp.qfac, clip};
-    if (sp.qfac != 0.0) nb_accumulate_kernel<true><<<count, kThreads, 0, st>>>(A);
-    else                nb_accumulate_kernel<false><<<count, kThreads, 0, st>>>(A);
+    cudaError_t err = cudaMemsetAsync(ticket, 0, sizeof(unsigned), st);
+    if (err != cudaSuccess) return err;
+    AccArgs A{crd, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, epart, nullptr, nullptr,
+              ticket, t0, count, S, nb_effective_cut2(sp), sp.krep, sp.qfac, clip};
+    const long long warps = 8LL * count;
+    const int grid = (int)std::min<long long>((warps + kForceWarps - 1) / kForceWarps, 5LL * sms);
+    launch_force(A, grid, st);
+    nb_energy_kernel<<<(count + 127) / 128, 128, 0, st>>>(epart, e_nb, t0, count);
     return cudaGetLastError();
 }
 
 // ---- the fused tail of the step ---------------------------------------------------------------------
 // NB accumulate + clip (master.cpp:297-322), then update_Velocities and update_Coordinates
-// (edmd.cpp:289-327) with the clipped force still on chip.  Other CTAs read a tetrad's coordinates as
-// a partner while it is being integrated, so the new coordinates go to a SECOND buffer (I.crd_out); the
-// next ED pass reads them from there.
+// (edmd.cpp:289-327).  Other CTAs read a tetrad's coordinates as a partner while it is being integrated, so
+// the new coordinates go to a SECOND buffer (I.crd_out); the next ED pass reads them from there.
 //
 // Almost every tetrad has no flagged pair, and then the tail is a pure streaming update.
-//   mark_tetrads_kernel     flagged pair -> both ends marked; the first marker of an owned tetrad appends
-//                           it to a compact list (the order of the list varies from run to run, each
-//                           tetrad's result does not depend on it);
-//   finish_unmarked_kernel  lean integrate for unmarked tetrads (few registers, no adjacency walk);
-//   finish_marked_kernel    a grid sized for the SMs walks the compact list, one CTA per marked tetrad.
+//   mark_tetrads_kernel   flagged pair -> both ends marked; the first marker of an owned tetrad appends it to
+//                         a compact list (the order of the list varies from run to run, each tetrad's result
+//                         does not depend on it);
+//   nb_force_kernel       the exact force pass over (marked tetrad, slot group) items, see above;
+//   finish_kernel         one CTA per owned tetrad: velocity + coordinate update, with the clipped NB force
+//                         and the pair energies read back for marked tetrads and zero for the others.
 __global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* pairs, long long np, int* mark,
                                     int* list, unsigned* count, int t0, int t1) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -880,63 +901,59 @@ __global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* p
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const int* mark,
-                                                                    unsigned char* dirty, double* fnb, double* e_nb) {
+__global__ void __launch_bounds__(kThreads, 4) finish_kernel(IntArgs I, const int* mark, unsigned char* dirty,
+                                                           double* fnb, const double* epart, double* e_nb) {
     __shared__ double red[1][kWarps];
     const int t = I.t0 + blockIdx.x;
-    if (mark[t]) return;
     const int S = I.ps.S;
-    if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
-        for (int k = threadIdx.x; k < 3 * S; k += blockDim.x) fnb[(size_t)t * 3 * S + k] = 0.0;
-        if (threadIdx.x == 0) { e_nb[2 * (size_t)t] = 0.0; e_nb[2 * (size_t)t + 1] = 0.0; dirty[t] = 0; }
+    const int tid = threadIdx.x;
+    double f[3] = {0.0, 0.0, 0.0};
+    if (mark[t]) {
+        if (tid < I.ps.na[I.param_id[t]]) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) f[c] = fnb[(size_t)t * 3 * S + c * S + tid];
+        }
+        if (tid == 0) {
+            double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { e0 += epart[((size_t)t * 8 + w) * 2]; e1 += epart[((size_t)t * 8 + w) * 2 + 1]; }
+            e_nb[2 * (size_t)t] = e0; e_nb[2 * (size_t)t + 1] = e1;
+            dirty[t] = 1;
+        }
+    } else if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
+        for (int k = tid; k < 3 * S; k += blockDim.x) fnb[(size_t)t * 3 * S + k] = 0.0;
+        if (tid == 0) { e_nb[2 * (size_t)t] = 0.0; e_nb[2 * (size_t)t + 1] = 0.0; dirty[t] = 0; }
     }
-    const double zero[3] = {0.0, 0.0, 0.0};
-    integrate_tetrad(I, t, zero, red);
-}
-
-template <bool HAS_Q>
-__global__ void __launch_bounds__(kThreads, 2) finish_marked_kernel(AccArgs A, IntArgs I, const int* list,
-                                                                  const unsigned* count, unsigned char* dirty) {
-    __shared__ AccSmem sm;
-    __shared__ double red[1][kWarps];
-    const unsigned total = *count;
-    for (unsigned i = blockIdx.x; i < total; i += gridDim.x) {
-        const int t = list[i];
-        double fr[3];
-        nb_accumulate_tetrad<HAS_Q>(A, t, sm, fr);
-        if (threadIdx.x == 0) dirty[t] = 1;
-        integrate_tetrad(I, t, fr, red);
-    }
+    integrate_tetrad(I, t, f, red);
 }
 
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
                                    const unsigned long long* hit, const int2* pairs, long long np, const long long* adj_off,
                                    const int* adj_partner, const int* adj_pair, const int* perm,
-                                   const unsigned long long* grp, double* fnb, double* e_nb,
+                                   const unsigned long long* grp, double* fnb, double* e_nb, double* epart,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
                                    const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
                                    int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    // mark[0..n) flags, then the list counter, then the compact list of marked owned tetrads
+    // mark[0..n) flags, then the list counter and the work-item counter, then the compact list of marked tetrads
     unsigned* cnt = reinterpret_cast<unsigned*>(mark + n);
-    int* list = mark + n + 1;
-    cudaError_t err = cudaMemsetAsync(mark, 0, sizeof(int) * ((size_t)n + 1), st);
+    unsigned* ticket = reinterpret_cast<unsigned*>(mark + n + 1);
+    int* list = mark + n + 2;
+    cudaError_t err = cudaMemsetAsync(mark, 0, sizeof(int) * ((size_t)n + 2), st);
     if (err != cudaSuccess) return err;
     if (np > 0) {
         long long blocks = (np + 255) / 256;
         if (blocks > sms * 16) blocks = sms * 16;
         mark_tetrads_kernel<<<(int)blocks, 256, 0, st>>>(hit, pairs, np, mark, list, cnt, t0, t0 + count);
+        // the number of marked tetrads is only known on the device: a grid that fills the SMs draws work items
+        AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, epart, list, cnt,
+                  ticket, t0, count, S, nb_effective_cut2(sp), sp.krep, sp.qfac, 1};
+        const long long warps = 8LL * count;
+        const int grid = (int)std::min<long long>((warps + kForceWarps - 1) / kForceWarps, 5LL * sms);
+        launch_force(A, grid, st);
     }
-    AccArgs A{crd_ro, natoms, param_id, chg, hit, adj_off, adj_partner, adj_pair, perm, grp, fnb, e_nb, t0, S,
-              nb_effective_cut2(sp), sp.krep, sp.qfac, 1};
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
-    finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
-    if (np > 0) {
-        // the number of marked tetrads is only known on the device: a grid that fills the SMs walks the list
-        const int grid = count < 4 * sms ? count : 4 * sms;
-        if (sp.qfac != 0.0) finish_marked_kernel<true><<<grid, kThreads, 0, st>>>(A, I, list, cnt, dirty);
-        else                finish_marked_kernel<false><<<grid, kThreads, 0, st>>>(A, I, list, cnt, dirty);
-    }
+    finish_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, epart, e_nb);
     return cudaGetLastError();
 }
 

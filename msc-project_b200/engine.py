@@ -562,9 +562,10 @@ class EngineGroup:
 def _nb_stats(self) -> dict:
     """Counts from the last NB pass: flagged tetrad pairs, marked (owned) tetrads, 32 x 32 atom blocks the
     force pass evaluates, tetrad pairs selected by the bounding-sphere tests."""
-    out = (C.c_longlong * 4)()
+    out = (C.c_longlong * 5)()
     self._ck(self.lib.edmd_nb_stats_ex(self.h, out))
-    return dict(flagged_pairs=out[0], marked_tetrads=out[1], force_blocks=out[2], selected_pairs=out[3])
+    return dict(flagged_pairs=out[0], marked_tetrads=out[1], force_blocks=out[2], selected_pairs=out[3],
+                sphere_blocks=out[4])
 
 
 Engine.nb_stats = _nb_stats

@@ -16,14 +16,18 @@ def run(*args, env=None):
 
 
 def test_reference_arm_prints_the_contract_line():
-    r = run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-budget", "0.5")
+    r = run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "500")
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "tetrad_pair_interactions_per_sec" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["unit"] == "tetrad-pairs/s" and d["steps"] == 1 and d["dtype"] == "f64"
-    assert d["config"]["tetrad_pairs"] == 494500 and "C1" in d["config"]["workload"]
+    assert d["config"]["tetrad_pairs"] == 400005 and d["config"]["tetrads"] == 100000 and "C3" in d["config"]["workload"]
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    assert d["config"] == bench.config_dict(400005)          # the GPU arm prints the same dict
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -31,7 +35,7 @@ def test_reference_arm_prints_the_contract_line():
 
 
 def test_reference_arm_other_ranks_exit_quietly():
-    r = run("--impl", "reference", "--steps", "1", "--warmup", "0", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    r = run("--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-sample", "500", env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
@@ -66,3 +70,16 @@ def test_clock_sampler_parses_nvidia_smi_lines():
     cs.t_begin, cs.t_end = now + 0.15, now + 0.16            # a 10 ms region: only one sample inside
     c = cs.stop()
     assert c["window"].startswith("whole run") and c["samples"] == 5 and "hw_slowdown" in c["reasons"]
+
+
+def test_ring_pair_count_equals_the_oracle_list():
+    """bench.ring_pair_count (used by both arms for the workload's pair count) == the reference pair list."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import importlib
+    import pyoracle
+    bench = importlib.import_module("bench")
+    pkg = importlib.import_module("msc-project_b200")
+    for n in (90, 400, 1000):
+        s = pkg.make_ring(n, kind="ring")
+        o = pyoracle.Oracle(s, "port")
+        assert o.build_pairs() == bench.ring_pair_count(s)
