@@ -172,6 +172,9 @@ struct edmd_engine {
     double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
     cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
     cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
+    cudaStream_t st_rng = nullptr;                  // edmd_step: the random-term generator beside the ED / distance kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool rng_branch = true;
     // asynchronous output (edmd_snapshot_begin / _wait): device -> caller buffers on a side stream
     cudaStream_t st_out = nullptr;
     cudaEvent_t ev_staged = nullptr, ev_snap[2] = {nullptr, nullptr};
@@ -466,7 +469,7 @@ int do_finish(edmd_engine* e) {
                                   e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->d_epart, e->ps,
                                   e->vel, e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty,
                                   e->n, e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
-        timer_end(e, T_ACC, e->np > 0 ? 3 : 1);
+        timer_end(e, T_ACC, e->np > 0 ? 4 : 1);
         e->latest_in_crd2 = true;
     }
     // Peer mode: the masks were stored by every rank's distance kernel; now that this rank has consumed them
@@ -485,7 +488,10 @@ int ensure_noise(edmd_engine* e) {
     e->noise_valid = true;
     return 0;
 }
-int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before, const long* calls_dev = nullptr) {
+int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before, const long* calls_dev = nullptr,
+              cudaStream_t on = nullptr) {
+    const bool side = on != nullptr;          // the step runs the generator on a branch beside the ED / distance kernels
+    if (!on) on = e->st;
     if (mode == 0) {
         if (!e->rnd_zero) {
             CK(cudaMemsetAsync(e->rnd, 0, sizeof(double) * (size_t)e->n * 3 * e->S, e->st));
@@ -495,10 +501,10 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before,
     }
     if (mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown (0 = off, 1 = reference stream)", mode);
     if (int rc = ensure_noise(e)) return rc;
-    timer_begin(e, T_RNG);
+    if (!side) timer_begin(e, T_RNG);
     CK(launch_random_terms(e->ps, e->d_noise, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
-                           calls_before + e->t0, calls_dev, e->st));
-    timer_end(e, T_RNG, 1);
+                           calls_before + e->t0, calls_dev, on));
+    if (!side) timer_end(e, T_RNG, 1); else e->launches++;
     e->rnd_zero = false;
     return 0;
 }
@@ -558,6 +564,9 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
     e->device = device;
     cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
     CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&e->st_rng, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     // EDMD::EDMD defaults (edmd.cpp:23-43)
     e->sp = SimParams{0.002 * 20.455, 2.0 / 20.455, 0.2 * 20.455, 300.0, 0.002 * 300.0, 30.0, 10.0, 5.0, 100.0, 0.0};
     if (p) {
@@ -577,6 +586,7 @@ void edmd_destroy(edmd_engine* e) {
     if (e->span0) { cudaEventDestroy(e->span0); cudaEventDestroy(e->span1); }
     for (cudaEvent_t ev : e->marks) cudaEventDestroy(ev);
     if (e->st_copy) cudaStreamDestroy(e->st_copy);
+    if (e->st_rng) { cudaStreamDestroy(e->st_rng); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_join); }
     if (e->st_out) { cudaStreamDestroy(e->st_out); cudaEventDestroy(e->ev_staged); cudaEventDestroy(e->ev_snap[0]); cudaEventDestroy(e->ev_snap[1]); }
     if (e->ev_crd_in) { cudaEventDestroy(e->ev_crd_in); cudaEventDestroy(e->ev_vel_in); }
     if (e->st) cudaStreamDestroy(e->st);
@@ -1243,10 +1253,25 @@ int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
 // when every owner's re-embedded coordinates exist: barrier, then pull the non-owned tetrads this rank reads;
 // (2) after the distance pass, whose kernels stored their masks into every rank's buffer: barrier, then the
 // owners' force pass.  Both are kernels on the engine stream, so the whole sharded step is graph-captured.
+//
+// The random terms depend on nothing but the call counter and are consumed only by the final update, and their
+// kernel is bound by instruction issue while the distance pass waits on memory: the generator runs on a
+// second stream (a parallel branch of the captured graph) and joins before the finish kernel.
 static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
+    const bool fork = random_mode == 1 && !e->timing && e->rng_branch;
+    if (fork) {
+        if (int rc = ensure_noise(e)) return rc;      // (its table is built on the main stream, before the fork)
+        CK(cudaEventRecord(e->ev_fork, e->st));       // after the previous step's finish kernel, which read e->rnd
+        CK(cudaStreamWaitEvent(e->st_rng, e->ev_fork, 0));
+        if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev, e->st_rng)) return rc;
+        if (calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st_rng)); e->launches++; }
+        CK(cudaEventRecord(e->ev_join, e->st_rng));
+    }
     if (int rc = do_ed(e)) return rc;
-    if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
-    if (random_mode == 1 && calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
+    if (!fork) {
+        if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
+        if (random_mode == 1 && calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
+    }
     if (e->peer_mode && !e->peer_replicated) {
         if (int rc = peer_barrier(e)) return rc;
         CK(launch_halo_pull(e->crd, e->d_crd_tbl, e->d_halo, e->halo_count, (e->n + e->world - 1) / e->world, e->S,
@@ -1255,7 +1280,15 @@ static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     }
     if (int rc = do_scan(e)) return rc;
     if (e->peer_mode) if (int rc = peer_barrier(e)) return rc;
+    if (fork) CK(cudaStreamWaitEvent(e->st, e->ev_join, 0));
     return do_finish(e);
+}
+
+int edmd_set_rng_branch(edmd_engine* e, int on) {
+    if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    e->rng_branch = on != 0;
+    drop_graph(e);
+    return 0;
 }
 
 int edmd_set_graph(edmd_engine* e, int on) {

@@ -443,10 +443,11 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
         }
         mbar_wait(&bar, phase);
         phase ^= 1;
-        {   // stage all 256 slots of the partner in its own compact-group order (empty slots never hit)
+        {   // stage the partner's slot groups that some masked block needs, in compact-group order (empty slots never hit)
             const int* PS = perm + (size_t)param_id[tsc] * kMaxStride;
 #pragma unroll
             for (int r = 0; r < kTI; r++) {
+                if (!((m >> (8 * r)) & 0xffull)) continue;      // partner group r takes part in no masked block
                 const int slot = lane + kScanThreads * r;
                 const int a = PS[slot];
                 const bool real = a >= 0;
@@ -888,8 +889,10 @@ cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int
 //                         a compact list (the order of the list varies from run to run, each tetrad's result
 //                         does not depend on it);
 //   nb_force_kernel       the exact force pass over (marked tetrad, slot group) items, see above;
-//   finish_kernel         one CTA per owned tetrad: velocity + coordinate update, with the clipped NB force
-//                         and the pair energies read back for marked tetrads and zero for the others.
+//   finish_unmarked_kernel  one CTA per owned tetrad without a flagged pair: lean streaming velocity +
+//                         coordinate update (zero NB force), 6 CTAs per SM to keep HBM busy;
+//   finish_marked_kernel  the same update for the listed tetrads, with the clipped NB force and the pair
+//                         energies of the force pass read back.
 __global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* pairs, long long np, int* mark,
                                     int* list, unsigned* count, int t0, int t1) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -901,14 +904,30 @@ __global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* p
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) finish_kernel(IntArgs I, const int* mark, unsigned char* dirty,
-                                                           double* fnb, const double* epart, double* e_nb) {
+__global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const int* mark, unsigned char* dirty,
+                                                                    double* fnb, double* e_nb) {
     __shared__ double red[1][kWarps];
     const int t = I.t0 + blockIdx.x;
+    if (mark[t]) return;
+    const int S = I.ps.S;
+    if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
+        for (int k = threadIdx.x; k < 3 * S; k += blockDim.x) fnb[(size_t)t * 3 * S + k] = 0.0;
+        if (threadIdx.x == 0) { e_nb[2 * (size_t)t] = 0.0; e_nb[2 * (size_t)t + 1] = 0.0; dirty[t] = 0; }
+    }
+    const double zero[3] = {0.0, 0.0, 0.0};
+    integrate_tetrad(I, t, zero, red);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) finish_marked_kernel(IntArgs I, const int* list, const unsigned* count,
+                                                                  unsigned char* dirty, const double* fnb,
+                                                                  const double* epart, double* e_nb) {
+    __shared__ double red[1][kWarps];
     const int S = I.ps.S;
     const int tid = threadIdx.x;
-    double f[3] = {0.0, 0.0, 0.0};
-    if (mark[t]) {
+    const unsigned total = *count;
+    for (unsigned i = blockIdx.x; i < total; i += gridDim.x) {
+        const int t = list[i];
+        double f[3] = {0.0, 0.0, 0.0};
         if (tid < I.ps.na[I.param_id[t]]) {
 #pragma unroll
             for (int c = 0; c < 3; c++) f[c] = fnb[(size_t)t * 3 * S + c * S + tid];
@@ -920,11 +939,8 @@ __global__ void __launch_bounds__(kThreads, 4) finish_kernel(IntArgs I, const in
             e_nb[2 * (size_t)t] = e0; e_nb[2 * (size_t)t + 1] = e1;
             dirty[t] = 1;
         }
-    } else if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
-        for (int k = tid; k < 3 * S; k += blockDim.x) fnb[(size_t)t * 3 * S + k] = 0.0;
-        if (tid == 0) { e_nb[2 * (size_t)t] = 0.0; e_nb[2 * (size_t)t + 1] = 0.0; dirty[t] = 0; }
+        integrate_tetrad(I, t, f, red);
     }
-    integrate_tetrad(I, t, f, red);
 }
 
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
@@ -953,7 +969,11 @@ cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, cons
         launch_force(A, grid, st);
     }
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
-    finish_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, epart, e_nb);
+    finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
+    if (np > 0) {
+        const int grid = count < 4 * sms ? count : 4 * sms;
+        finish_marked_kernel<<<grid, kThreads, 0, st>>>(I, list, cnt, dirty, fnb, epart, e_nb);
+    }
     return cudaGetLastError();
 }
 

@@ -126,6 +126,7 @@ def load_library():
         "edmd_set_rng": (C.c_int, [E, C.c_long, C.c_int, C.c_long]),
         "edmd_step": (C.c_int, [E, C.c_int, C.c_int]),
         "edmd_set_graph": (C.c_int, [E, C.c_int]),
+        "edmd_set_rng_branch": (C.c_int, [E, C.c_int]),
         "edmd_sync": (C.c_int, [E]),
         "edmd_device_buffer": (C.c_int, [E, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
         "edmd_atom_stride": (C.c_int, [E]),
@@ -439,6 +440,9 @@ class Engine:
         """edmd_step_host: the host Tetrad block (self.block.crd / .vel) in, stepped, and back in place."""
         self._ck(self.lib.edmd_step_host(self.h, self.block.ptr, self.sys.n, nsteps, random_mode))
         return self.block.crd, self.block.vel
+
+    def set_rng_branch(self, on: bool):
+        self._ck(self.lib.edmd_set_rng_branch(self.h, int(on)))
 
     def set_graph(self, on: bool):
         self._ck(self.lib.edmd_set_graph(self.h, int(on)))
