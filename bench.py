@@ -118,6 +118,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
+def bind_near_gpu(local):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node the GPU hangs off:
+    host<->device copies that cross the socket interconnect run at a fraction of the PCIe rate.  Best effort."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id if hasattr(torch.cuda.get_device_properties(local), "pci_bus_id") else None
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        if bus is None:
+            return None
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return txt
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -358,6 +383,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the EDMD engine has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None      # (one rank: keep every host thread for the CPU baseline)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -450,7 +476,8 @@ def main():
            "ms_per_step": t_e2e * 1e3,
            "how": ("edmd_step_host: host Tetrad arrays (pinned) -> device, one step, device -> host Tetrad arrays" if world == 1 else
                    "per rank: edmd_set_state_owned (its block of the host arrays) -> sharded edmd_step -> edmd_get_state_owned; "
-                   "bytes are the total over ranks")}
+                   "bytes are the total over ranks"),
+           "host_cpus_rank0": numa}
 
     parity = None
     if world > 1:

@@ -333,6 +333,151 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
     }
 }
 
+// ---- two tetrads per warp ----------------------------------------------------------------------------
+// Same sums in the same order, but a warp carries TWO tetrads, one per half-warp: the per-atom terms are
+// produced 16 atoms at a time by each half into its own [10][17] shared tile, and the chains of both tetrads
+// advance together (lanes 0..9 and 16..25), so one chain instruction serves two tetrads.  Nothing else is
+// staged in shared memory — the coordinates are re-read from L1/L2 in each of the three passes, one block
+// ahead of their use — so a CTA needs 11 KB and the SM holds 64 tetrads in flight instead of 24: the chains are
+// bound by the latency of dependent adds, and twice the independent chains per issued instruction plus 2.7x
+// the tetrads in flight is what this layout buys.
+constexpr int kS2Warps = 4;
+constexpr int kS2Row = 17;
+struct Sup2Tile { double v[2][10][kS2Row]; };
+
+// s += row[0..cnt) (cnt <= 16), sequentially
+__device__ __forceinline__ double tile_chain16(double s, const double* row, int cnt) {
+    if (cnt == 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) v[u] = row[u];
+#pragma unroll
+        for (int u = 0; u < 16; u++) s = s + v[u];
+    } else {
+        for (int i = 0; i < cnt; i++) s = s + row[i];
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A) {
+    __shared__ Sup2Tile tiles[kS2Warps];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int half = lane >> 4, hl = lane & 15, base = lane & 16;
+    const int e = (blockIdx.x * kS2Warps + warp) * 2 + half;
+    const bool live = e < A.count;                       // the last warp may carry a single tetrad
+    double (*tile)[kS2Row] = tiles[warp].v[half];
+    const int S = A.ps.S;
+    const int t = A.t0 + (live ? e : A.count - 1);       // (a dead half reads a valid tetrad and writes nothing)
+    const int ps = A.param_id[t];
+    const int na = live ? A.ps.na[ps] : 0;
+    const int na_max = max(na, __shfl_xor_sync(full, na, 16));   // both halves walk the same number of blocks
+    const double* X = A.crd + (size_t)t * 3 * S;
+    const double* AV = A.ps.avg + (size_t)ps * 3 * S;
+    const double* PRE = A.ps.pre + 4 * (size_t)ps;
+    const double ca0 = PRE[0], ca1 = PRE[1], ca2 = PRE[2], g_ref = PRE[3];
+
+    // pass 1 — CenterCoords, qcprot.c:370-379: sums in atom order, then divide by len
+    double cx0, cx1, cx2;
+    {
+        double acc = 0.0;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
+        if (hl < na) { p0 = X[hl]; p1 = X[S + hl]; p2 = X[2 * S + hl]; }
+        for (int b = 0; b < na_max; b += 16) {
+            const int i = b + hl;
+            const double x0 = p0, x1 = p1, x2 = p2;
+            if (i + 16 < na) { p0 = X[i + 16]; p1 = X[S + i + 16]; p2 = X[2 * S + i + 16]; }
+            tile[0][hl] = x0; tile[1][hl] = x1; tile[2][hl] = x2;
+            __syncwarp();
+            const int cnt = na - b < 16 ? na - b : 16;
+            if (hl < 3 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt);
+            __syncwarp();
+        }
+        const double c = na > 0 ? acc / na : 0.0;
+        cx0 = __shfl_sync(full, c, base); cx1 = __shfl_sync(full, c, base + 1); cx2 = __shfl_sync(full, c, base + 2);
+    }
+
+    // pass 2 — InnerProduct, qcprot.c:132-157: chains 0-8 the 3x3 products avg_c (x) x_c, chain 9 the norm of x_c
+    double R[9];
+    {
+        double acc = 0.0;
+        double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0, px0 = 0.0, px1 = 0.0, px2 = 0.0;
+        if (hl < na) {
+            pa0 = AV[hl]; pa1 = AV[S + hl]; pa2 = AV[2 * S + hl];
+            px0 = X[hl]; px1 = X[S + hl]; px2 = X[2 * S + hl];
+        }
+        for (int b = 0; b < na_max; b += 16) {
+            const int i = b + hl;
+            const double r0 = pa0, r1 = pa1, r2 = pa2, y0 = px0, y1 = px1, y2 = px2;
+            if (i + 16 < na) {
+                pa0 = AV[i + 16]; pa1 = AV[S + i + 16]; pa2 = AV[2 * S + i + 16];
+                px0 = X[i + 16]; px1 = X[S + i + 16]; px2 = X[2 * S + i + 16];
+            }
+            double v[10];
+#pragma unroll
+            for (int k = 0; k < 10; k++) v[k] = 0.0;
+            if (i < na) {
+                const double a0 = r0 - ca0, a1 = r1 - ca1, a2 = r2 - ca2;
+                const double x0 = y0 - cx0, x1 = y1 - cx1, x2 = y2 - cx2;     // centred copies, qcprot.c:382-386
+                v[0] = a0 * x0; v[1] = a0 * x1; v[2] = a0 * x2;
+                v[3] = a1 * x0; v[4] = a1 * x1; v[5] = a1 * x2;
+                v[6] = a2 * x0; v[7] = a2 * x1; v[8] = a2 * x2;
+                v[9] = (x0 * x0 + x1 * x1) + x2 * x2;
+            }
+#pragma unroll
+            for (int k = 0; k < 10; k++) tile[k][hl] = v[k];
+            __syncwarp();
+            const int cnt = na - b < 16 ? na - b : 16;
+            if (hl < 10 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt);
+            __syncwarp();
+        }
+        double m[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) m[j] = __shfl_sync(full, acc, base + j);
+        const double g_x = __shfl_sync(full, acc, base + 9);
+        qcp_rotation(R, m, (g_ref + g_x) * 0.5);
+    }
+
+    // pass 3 — offset-vector terms on the UNCENTRED arrays, edmd.cpp:97-101
+    double off = 0.0;
+    {
+        double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0, px0 = 0.0, px1 = 0.0, px2 = 0.0;
+        if (hl < na) {
+            pa0 = AV[hl]; pa1 = AV[S + hl]; pa2 = AV[2 * S + hl];
+            px0 = X[hl]; px1 = X[S + hl]; px2 = X[2 * S + hl];
+        }
+        for (int b = 0; b < na_max; b += 16) {
+            const int i = b + hl;
+            const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
+            if (i + 16 < na) {
+                pa0 = AV[i + 16]; pa1 = AV[S + i + 16]; pa2 = AV[2 * S + i + 16];
+                px0 = X[i + 16]; px1 = X[S + i + 16]; px2 = X[2 * S + i + 16];
+            }
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
+            if (i < na) {
+                w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
+                w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
+                w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
+            }
+            tile[0][hl] = w0; tile[1][hl] = w1; tile[2][hl] = w2;
+            __syncwarp();
+            const int cnt = na - b < 16 ? na - b : 16;
+            if (hl < 3 && cnt > 0) off = tile_chain16(off, tile[hl], cnt);
+            __syncwarp();
+        }
+    }
+
+    if (!live) return;
+    double* out = A.sup + (size_t)t * kSupWords;
+#pragma unroll
+    for (int j = 0; j < 9; j++) if (hl == j) out[j] = R[j];
+    if (hl < 3) {
+        out[9 + hl] = off / na;                                              // edmd.cpp:102
+        out[12 + hl] = hl == 0 ? ca0 : hl == 1 ? ca1 : ca2;
+        out[15 + hl] = hl == 0 ? cx0 : hl == 1 ? cx1 : cx2;
+    }
+}
+
 // Sum 12 per-lane values over the warp with a halving butterfly: at each of the 5 stages a lane
 // keeps half of its values and hands the other half to its partner, so the 12 sums cost
 // 6+3+2+1+1 = 13 adds and exchanges per lane instead of 12 x 5.  On return lane l holds the warp
@@ -678,10 +823,11 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
 }
 
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
-                             cudaStream_t st) {
+                             int variant, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
-    superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
+    if (variant == 1) superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
+    else              superpose2_kernel<<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
     return cudaGetLastError();
 }
 

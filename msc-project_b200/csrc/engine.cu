@@ -154,6 +154,7 @@ struct edmd_engine {
     long calls = 0;
 
     int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
+    int sup_variant = 0; // superposition kernel: 0 two tetrads per warp, 1 one tetrad per warp (EDMD_SUPERPOSE=1)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
     bool use_graph = true, graph_valid = false;
@@ -175,6 +176,7 @@ struct edmd_engine {
     cudaStream_t st_rng = nullptr;                  // edmd_step: the random-term generator beside the ED / distance kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool rng_branch = true;
+    int rng_ctas_per_sm = 4;
     // asynchronous output (edmd_snapshot_begin / _wait): device -> caller buffers on a side stream
     cudaStream_t st_out = nullptr;
     cudaEvent_t ev_staged = nullptr, ev_snap[2] = {nullptr, nullptr};
@@ -215,6 +217,7 @@ void drop_graph(edmd_engine* e);
 void close_peers(edmd_engine* e);
 void free_system(edmd_engine* e) {
     drop_graph(e);
+    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
     close_peers(e);
     cudaFree(e->d_hitx); e->d_hitx = nullptr; e->hitx_cap = 0;
     cudaFree(e->d_flags); cudaFree(e->d_epoch); cudaFree(e->d_peer_err);
@@ -374,7 +377,7 @@ int rebuild_halo(edmd_engine* e) {
 
 void drop_graph(edmd_engine* e) {
     e->need_valid = false;   // every caller changes the pair list, the shard or the scan mode
-    if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+    // the executable graph is kept: the next capture tries to update it in place (edmd_step)
     if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; }
     e->graph_valid = false;
 }
@@ -410,7 +413,7 @@ int do_ed(edmd_engine* e) {
     // share it: worth it when sets are shared (replicated DNA), not when every tetrad has its own.
     const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && (long long)e->n >= 8LL * e->P);
     timer_begin(e, T_SUP);
-    CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->st));
+    CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->st));
     timer_end(e, T_SUP, 0);
     CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
                          e->t1 - e->t0, e->sp.scaled, warp, e->st));
@@ -502,8 +505,10 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before,
     if (mode != 1) return fail(EDMD_ERR_ARG, "random mode %d unknown (0 = off, 1 = reference stream)", mode);
     if (int rc = ensure_noise(e)) return rc;
     if (!side) timer_begin(e, T_RNG);
+    // beside other kernels: a resident grid of rng_ctas_per_sm CTAs per SM, so that the generator takes a fixed
+    // slice of every SM for most of the step instead of the whole machine for a part of it
     CK(launch_random_terms(e->ps, e->d_noise, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
-                           calls_before + e->t0, calls_dev, on));
+                           calls_before + e->t0, calls_dev, side ? e->sms * e->rng_ctas_per_sm : 0, on));
     if (!side) timer_end(e, T_RNG, 1); else e->launches++;
     e->rnd_zero = false;
     return 0;
@@ -563,8 +568,10 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
     edmd_engine* e = new edmd_engine();
     e->device = device;
     cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
-    CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&e->st_rng, cudaStreamNonBlocking));
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));     // (numerically lower = more urgent)
+    CK(cudaStreamCreateWithPriority(&e->st, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&e->st_rng, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     // EDMD::EDMD defaults (edmd.cpp:23-43)
@@ -574,6 +581,10 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
         e->sp.scaled = p->scaled; e->sp.mole_cutoff = p->mole_Cutoff; e->sp.atom_cutoff = p->atom_Cutoff;
         e->sp.mole_least = p->mole_Least;
     }
+    // tuning switches for A/B measurements (none changes a result bit)
+    if (const char* v = getenv("EDMD_SUPERPOSE")) e->sup_variant = atoi(v) == 1 ? 1 : 0;
+    if (const char* v = getenv("EDMD_RNG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 16) e->rng_ctas_per_sm = k; }
+    if (const char* v = getenv("EDMD_RNG_BRANCH")) e->rng_branch = atoi(v) != 0;
     *out = e;
     return 0;
 }
@@ -1138,6 +1149,7 @@ int edmd_set_shard(edmd_engine* e, int t0, int t1, long long p0, long long p1) {
     if (t0 < 0 || t1 > e->n || t0 > t1) return fail(EDMD_ERR_ARG, "tetrad shard [%d,%d) out of range", t0, t1);
     if (p0 < 0 || p0 > p1 || (e->have_pairs && p1 > e->np)) return fail(EDMD_ERR_ARG, "pair shard out of range");
     CK(cudaSetDevice(e->device));
+    if (e->shard_pairs_custom && t0 == e->t0 && t1 == e->t1 && p0 == e->p0 && p1 == e->p1) return 0;
     if (int rc = normalize(e)) return rc;
     const bool range_changed = (t0 != e->t0 || t1 != e->t1);
     drop_graph(e);
@@ -1286,7 +1298,9 @@ static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
 
 int edmd_set_rng_branch(edmd_engine* e, int on) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
+    if (on < 0 || on > 16) return fail(EDMD_ERR_ARG, "rng branch: 0 = off, 1 = on, 2..16 = on with that many generator CTAs per SM");
     e->rng_branch = on != 0;
+    if (on >= 2) e->rng_ctas_per_sm = on;
     drop_graph(e);
     return 0;
 }
@@ -1338,7 +1352,15 @@ int edmd_step(edmd_engine* e, int nsteps, int random_mode) {
         e->rnd_zero = random_mode == 0 ? zero_flag : false;
         if (rc) { if (e->graph) { cudaGraphDestroy(e->graph); e->graph = nullptr; } return rc; }
         CK(end);
-        CK(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+        // a rebuilt pair list changes kernel arguments and grid sizes but rarely the shape of the graph:
+        // patch the executable graph in place when that works, instantiate a new one otherwise
+        bool updated = false;
+        if (e->graph_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(e->graph_exec, e->graph, &info) == cudaSuccess) updated = true;
+            else { cudaGetLastError(); cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        }
+        if (!updated) CK(cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
         e->graph_valid = true; e->graph_random_mode = random_mode;
         e->latest_in_crd2 = true;
     }

@@ -14,8 +14,9 @@ inline double nb_effective_cut2(const SimParams& sp) {
 }
 
 constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scratch (ed.cu)
+// variant: 0 = two tetrads per warp (default), 1 = one tetrad per warp with the coordinates staged in shared memory
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
-                             cudaStream_t st);
+                             int variant, cudaStream_t st);
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                               bool use_warp_kernel, cudaStream_t st);
@@ -89,7 +90,7 @@ cudaError_t build_halo_list(const int2* pairs, long long np, long long p0, long 
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                const long* calls_dev, cudaStream_t st);
+                                const long* calls_dev, int max_ctas /* 0: one tetrad per warp */, cudaStream_t st);
 cudaError_t launch_ps_precompute(const ParamSets& ps, int P, double* pre, cudaStream_t st);
 cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const SimParams& sp, cudaStream_t st);
 cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st);

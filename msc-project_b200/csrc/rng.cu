@@ -58,8 +58,10 @@ struct RngArgs {
 
 __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= A.count) return;
+    // warps walk the tetrads with a grid stride: a full grid gives one tetrad per warp; the step's side branch
+    // launches a small resident grid instead, which leaves most of every SM to the kernels it runs beside
+    const int warps = gridDim.x * (blockDim.x >> 5);
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < A.count; w += warps) {
     const int t = A.t0 + w;
     const int ps = A.param_id[t];
     const int S = A.ps.S;
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
         }
         k += __popc(acc);
     }
+    }   // tetrads of this warp
 }
 
 // noise[p][c][a] = sqrt(2*gamma*kT*m/dt), edmd.cpp:184 — one table per parameter set instead of one
@@ -142,11 +145,13 @@ cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const 
 
 cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                const long* calls_dev, cudaStream_t st) {
+                                const long* calls_dev, int max_ctas, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     RngArgs A{ps, noise, param_id, rnd, t0, count, sp.gamma, sp.scaled, sp.dt, time0, rank, calls_before, calls_dev};
     const int wpb = 4;
-    random_terms_kernel<<<(count + wpb - 1) / wpb, wpb * 32, 0, st>>>(A);
+    int grid = (count + wpb - 1) / wpb;
+    if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+    random_terms_kernel<<<grid, wpb * 32, 0, st>>>(A);
     return cudaGetLastError();
 }
 

@@ -207,6 +207,7 @@ class ShardedEngine:
         self.halo = (not self.replicate) if halo is None else (bool(halo) and not self.replicate)
         self.halo_plan = None
         self._attached = False
+        self._complete = False                   # every rank's copy of the coordinates is complete (after merge / finish)
         self.plan = None
         self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
 
@@ -297,7 +298,7 @@ class ShardedEngine:
             self._attached = False
 
     def _build_native(self) -> int:
-        if self._attached:
+        if self._attached and not self._complete:
             self.b.peer_gather(1)                # owners' coordinates -> every rank
         try:
             npairs = self.b.build_pairlist()
@@ -312,7 +313,6 @@ class ShardedEngine:
         if self.replicate:
             self.plan.t0, self.plan.t1 = 0, self.n
         self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)
-        self.b.engine_set_rng(self.time0, self.rng_rank, self.calls)
         return npairs
 
     def close(self):
@@ -327,6 +327,7 @@ class ShardedEngine:
 
     def step(self, nsteps=1, random_mode=0):
         if self.native:                          # one call: the sharded step is inside the engine
+            self._complete = False
             self.b.engine_step(nsteps, random_mode)
             if random_mode == 1:
                 self.calls += nsteps * self.n
@@ -351,6 +352,7 @@ class ShardedEngine:
         if self.native:
             self.b.peer_gather(3)
             self.b.merge()
+            self._complete = True
             return
         with self.b.stream_ctx():
             self.gather_coordinates(full=True)
@@ -362,6 +364,7 @@ class ShardedEngine:
         if self.native:
             self.b.peer_gather(7)
             self.b.sync()
+            self._complete = True
             return
         with self.b.stream_ctx():
             self.gather_coordinates(full=True)
