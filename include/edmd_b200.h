@@ -242,8 +242,9 @@ int edmd_step_host(edmd_engine* e, edmd_tetrad* tets, int n, int nsteps, int ran
 int edmd_snapshot_begin(edmd_engine* e, int ticket, double* crd, double* vel, double* obs);
 int edmd_snapshot_wait(edmd_engine* e, int ticket);
 long long edmd_state_doubles(edmd_engine* e);
-/* edmd_step runs the random-term generator on a parallel branch beside the ED and distance kernels (on by
- * default; off: one stream, kernels back to back).  Same results either way. */
+/* Optional: run the random-term generator on a parallel branch of the step graph beside the ED and distance
+ * kernels (0 = off, the default: measured slower on B200; 1 = on; 2..16 = on with that many
+ * generator CTAs resident per SM).  Same results either way. */
 int edmd_set_rng_branch(edmd_engine* e, int on);
 /* edmd_step replays a CUDA graph of one step (on by default; off: plain kernel launches). */
 int edmd_set_graph(edmd_engine* e, int on);

@@ -175,8 +175,8 @@ struct edmd_engine {
     cudaEvent_t ev_crd_in = nullptr, ev_vel_in = nullptr;
     cudaStream_t st_rng = nullptr;                  // edmd_step: the random-term generator beside the ED / distance kernels
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool rng_branch = true;
-    int rng_ctas_per_sm = 4;
+    bool rng_branch = false;   // measured slower than back-to-back kernels: off unless asked for
+    int rng_ctas_per_sm = 16;
     // asynchronous output (edmd_snapshot_begin / _wait): device -> caller buffers on a side stream
     cudaStream_t st_out = nullptr;
     cudaEvent_t ev_staged = nullptr, ev_snap[2] = {nullptr, nullptr};
@@ -1266,9 +1266,11 @@ int edmd_set_rng(edmd_engine* e, long time0, int rank, long calls_before) {
 // (2) after the distance pass, whose kernels stored their masks into every rank's buffer: barrier, then the
 // owners' force pass.  Both are kernels on the engine stream, so the whole sharded step is graph-captured.
 //
-// The random terms depend on nothing but the call counter and are consumed only by the final update, and their
-// kernel is bound by instruction issue while the distance pass waits on memory: the generator runs on a
-// second stream (a parallel branch of the captured graph) and joins before the finish kernel.
+// The random terms depend on nothing but the call counter and are consumed only by the final update, so the
+// generator CAN run on a second stream (a parallel branch of the captured graph, edmd_set_rng_branch) and join
+// before the finish kernel.  Measured at 1e5 tetrads: 3.22-3.57 ms per step with the branch (any resident grid
+// size) against 3.16 ms back to back — every kernel of the step is bound by latency or issue and wants all the
+// warp slots of an SM, so co-running only divides them.  The branch is therefore off by default.
 static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     const bool fork = random_mode == 1 && !e->timing && e->rng_branch;
     if (fork) {

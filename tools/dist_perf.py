@@ -20,7 +20,9 @@ s = pkg.make_ring(n, kind=kind, laps=laps, lap_gap=gap)
 g = pkg.Engine(s, device=local)
 g.set_nb_consts(100.0, qfac)
 sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
-sh.set_rng(1000000000, 1, 0)
+sh.set_rng(1000000000, 1, 0); g.set_rng(1000000000, 1, 0)
+if world == 1:
+    sh.step = lambda k, mode: g.step(k, mode)      # one GPU: edmd_step (graph replay), the production entry point
 t0 = time.time(); npairs = sh.build_pairlist(); tb = time.time() - t0
 sh.step(3, random_mode); g.sync()
 if dist: dist.barrier()
