@@ -1,0 +1,5 @@
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t7.log 2>&1; tail -4 gpurun_out/r2_t7.log
+timeout 200 python tools/dist_perf.py 100000 50 1 2>&1 | tail -1
+timeout 100 python tools/dist_perf.py 12500 100 1 2>&1 | tail -1
+timeout 100 python tools/dist_perf.py 1000 200 0 2>&1 | tail -1
+timeout 200 python tools/dist_perf.py 100000 20 1 coil 2 40 2>&1 | tail -1

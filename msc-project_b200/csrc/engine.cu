@@ -290,7 +290,7 @@ int ensure_pair_capacity(edmd_engine* e, long long np) {
     e->d_pairs = nullptr; e->d_hit = nullptr; e->d_pmask = nullptr; e->pairs_cap = 0; e->pmask_cap = 0;
     CK(dev_alloc(&e->d_pairs, (size_t)cap));
     CK(dev_alloc(&e->d_hit, (size_t)cap));
-    CK(dev_alloc(&e->d_pmask, 2 * (size_t)cap + 2));   // counter slot + one {pair, mask} item per pair (nb.cu)
+    CK(dev_alloc(&e->d_pmask, 2 * (size_t)cap + 2));   // one {pair, mask} work item per pair (nb.cu)
     e->pmask_cap = cap;
     e->pairs_cap = cap;
     return 0;
@@ -431,11 +431,14 @@ int ensure_need(edmd_engine* e) {
 }
 int do_scan(edmd_engine* e) {
     const double cut_eff = nb_effective_cut2(e->sp);
+    // one memset for the per-step scratch of the NB phase: tetrad marks, marked-list counter, work-item counter,
+    // distance-pass item counter (nb.cu: launch_nb_finish_split)
+    CK(cudaMemsetAsync(e->d_mark, 0, sizeof(int) * ((size_t)e->n + 4), e->st));
     if (e->scan_mode == 4 && cut_eff >= 1e-3 && cut_eff < 1e6) {
         if (int rc = ensure_need(e)) return rc;
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
-                               e->d_gb, e->d_pmask, e->d_param_id, e->d_perm, e->d_need,
+                               e->d_gb, e->d_pmask, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->d_param_id, e->d_perm, e->d_need,
                                e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -461,7 +464,7 @@ int do_accumulate(edmd_engine* e) {
 }
 // accumulate + clip + velocity + coordinate update in one kernel (edmd_step, edmd_nb_finish)
 int do_integrate(edmd_engine* e, int do_vel, int do_crd);
-int do_finish(edmd_engine* e) {
+int do_finish(edmd_engine* e, long* bump = nullptr) {
     if (int rc = normalize(e)) return rc;
     if (!e->nb_clip) {   // unclipped forces requested: run the two unfused kernels
         if (int rc = do_accumulate(e)) return rc;
@@ -471,7 +474,7 @@ int do_finish(edmd_engine* e) {
         CK(launch_nb_finish_split(e->crd, e->d_natoms, e->d_param_id, e->d_chg, cur_hits(e), e->d_pairs, e->np, e->d_adj_off,
                                   e->d_adj_partner, e->d_adj_pair, e->d_perm, e->d_grp, e->fnb, e->e_nb, e->d_epart, e->ps,
                                   e->vel, e->crd2, e->fed, e->rnd_zero ? nullptr : e->rnd, e->temp, e->d_mark, e->d_dirty,
-                                  e->n, e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, e->st));
+                                  e->n, e->t0, e->t1 - e->t0, e->S, e->sms, e->sp, bump, (long)e->n, e->st));
         timer_end(e, T_ACC, e->np > 0 ? 4 : 1);
         e->latest_in_crd2 = true;
     }
@@ -789,7 +792,8 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(dev_alloc(&e->obs, 4 * (size_t)n));
     e->e_ed = e->obs; e->e_nb = e->obs + n; e->temp = e->obs + 3 * (size_t)n;
     CK(dev_alloc(&e->cen, 4 * (size_t)n));
-    CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 4)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(dev_alloc(&e->d_mark, 2 * (size_t)n + 8)); CK(dev_alloc(&e->d_dirty, (size_t)n));
+    CK(cudaMemsetAsync(e->d_mark, 0, sizeof(int) * (2 * (size_t)n + 8), e->st));
     CK(dev_alloc(&e->d_epart, 16 * (size_t)n));
     CK(cudaMemsetAsync(e->d_epart, 0, sizeof(double) * 16 * (size_t)n, e->st));
     CK(dev_alloc(&e->d_gb, (size_t)n * 36));
@@ -1284,7 +1288,7 @@ static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     if (int rc = do_ed(e)) return rc;
     if (!fork) {
         if (int rc = do_random(e, random_mode, e->time0, e->rank, e->calls, calls_dev)) return rc;
-        if (random_mode == 1 && calls_dev) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
+        if (random_mode == 1 && calls_dev && !e->nb_clip) { CK(launch_bump_counter(e->d_calls, (long)e->n, e->st)); e->launches++; }
     }
     if (e->peer_mode && !e->peer_replicated) {
         if (int rc = peer_barrier(e)) return rc;
@@ -1295,7 +1299,8 @@ static int one_step(edmd_engine* e, int random_mode, const long* calls_dev) {
     if (int rc = do_scan(e)) return rc;
     if (e->peer_mode) if (int rc = peer_barrier(e)) return rc;
     if (fork) CK(cudaStreamWaitEvent(e->st, e->ev_join, 0));
-    return do_finish(e);
+    // (the replayed graph's call counter advances inside the finish kernel, after the generator has read it)
+    return do_finish(e, (!fork && random_mode == 1 && calls_dev && e->nb_clip) ? e->d_calls : nullptr);
 }
 
 int edmd_set_rng_branch(edmd_engine* e, int on) {
@@ -1589,11 +1594,11 @@ int edmd_nb_stats_ex(edmd_engine* e, long long out[5]) {
     for (int t = e->t0; t < e->t1; t++) out[1] += marked[t];
     if (e->scan_mode == 4 && e->d_pmask) {
         unsigned cnt = 0;
-        CK(cudaMemcpy(&cnt, e->d_pmask, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&cnt, e->d_mark + e->n + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
         out[3] = cnt;
-        // work items {pair index, sphere mask} follow the 16-byte counter slot (nb.cu: CullItem)
+        // work items {pair index, sphere mask} (nb.cu: CullItem)
         std::vector<unsigned long long> items(2 * (size_t)cnt);
-        if (cnt) CK(cudaMemcpy(items.data(), e->d_pmask + 2, sizeof(unsigned long long) * items.size(), cudaMemcpyDeviceToHost));
+        if (cnt) CK(cudaMemcpy(items.data(), e->d_pmask, sizeof(unsigned long long) * items.size(), cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < cnt; i++) out[4] += __builtin_popcountll(items[2 * i + 1]);
     }
     return 0;

@@ -27,8 +27,8 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* mask, const int* param_id, const int* perm, const unsigned char* need,
-                                unsigned long long* const* peers, int world, cudaStream_t st);
+                                unsigned long long* items, unsigned* item_count, const int* param_id, const int* perm,
+                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st);
 cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
 // hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the
@@ -40,14 +40,16 @@ cudaError_t launch_nb_accumulate(const double* crd, const int* natoms, const int
                                  double* e_nb, double* epart, unsigned* ticket, int t0, int count, int S, int sms,
                                  const SimParams& sp, int clip, cudaStream_t st);
 
-// mark: int [2n + 2] scratch (flags, list counter, work-item counter, compact list of marked tetrads)
+// mark: int [2n + 4] scratch (flags, list counter, work-item counter, distance-pass item counter, pad, compact list
+// of marked tetrads); bump: the random-stream call counter to advance by bump_by (nullptr: none)
 cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, const int* param_id, const double* chg,
                                    const unsigned long long* hit, const int2* pairs, long long np, const long long* adj_off,
                                    const int* adj_partner, const int* adj_pair, const int* perm,
                                    const unsigned long long* grp, double* fnb, double* e_nb, double* epart,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
                                    const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
-                                   int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st);
+                                   int t0, int count, int S, int sms, const SimParams& sp, long* bump, long bump_by,
+                                   cudaStream_t st);
 
 cudaError_t launch_integrate(const ParamSets& ps, const int* param_id, double* vel, double* crd,
                              const double* fed, const double* rnd, const double* fnb, double* temp,

@@ -506,18 +506,15 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* work, const int* param_id, const int* perm, const unsigned char* need,
-                                unsigned long long* const* peers, int world, cudaStream_t st) {
+                                unsigned long long* work, unsigned* count, const int* param_id, const int* perm,
+                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
-    // work buffer: [0] the item counter (16-byte slot), then one CullItem per listed pair at most
-    unsigned* count = reinterpret_cast<unsigned*>(work);
-    CullItem* items = reinterpret_cast<CullItem*>(work + 2);
-    cudaError_t err = cudaMemsetAsync(count, 0, 16, st);
-    if (err != cudaSuccess) return err;
+    // work buffer: one CullItem per listed pair at most; the item counter was zeroed by the caller
+    CullItem* items = reinterpret_cast<CullItem*>(work);
     group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S, need);
     const long long want = p1 - p0;
     pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
@@ -905,9 +902,12 @@ __global__ void mark_tetrads_kernel(const unsigned long long* hit, const int2* p
 }
 
 __global__ void __launch_bounds__(kThreads, 6) finish_unmarked_kernel(IntArgs I, const int* mark, unsigned char* dirty,
-                                                                    double* fnb, double* e_nb) {
+                                                                    double* fnb, double* e_nb, long* bump, long bump_by) {
     __shared__ double red[1][kWarps];
     const int t = I.t0 + blockIdx.x;
+    // the random-stream call counter of the replayed step graph advances here (its reader, the generator
+    // kernel, ran earlier in the step)
+    if (bump && blockIdx.x == 0 && threadIdx.x == 0) *bump += bump_by;
     if (mark[t]) return;
     const int S = I.ps.S;
     if (dirty[t]) {   // forces left by an earlier step in which this tetrad had a flagged pair
@@ -949,14 +949,14 @@ cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, cons
                                    const unsigned long long* grp, double* fnb, double* e_nb, double* epart,
                                    const ParamSets& ps, double* vel, double* crd_out, const double* fed,
                                    const double* rnd, double* temp, int* mark, unsigned char* dirty, int n,
-                                   int t0, int count, int S, int sms, const SimParams& sp, cudaStream_t st) {
+                                   int t0, int count, int S, int sms, const SimParams& sp, long* bump, long bump_by,
+                                   cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
-    // mark[0..n) flags, then the list counter and the work-item counter, then the compact list of marked tetrads
+    // mark[0..n) flags, then the list counter, the work-item counter and the distance pass's item counter (all
+    // zeroed together before the distance pass, engine.cu: do_scan), then the compact list of marked tetrads
     unsigned* cnt = reinterpret_cast<unsigned*>(mark + n);
     unsigned* ticket = reinterpret_cast<unsigned*>(mark + n + 1);
-    int* list = mark + n + 2;
-    cudaError_t err = cudaMemsetAsync(mark, 0, sizeof(int) * ((size_t)n + 2), st);
-    if (err != cudaSuccess) return err;
+    int* list = mark + n + 4;
     if (np > 0) {
         long long blocks = (np + 255) / 256;
         if (blocks > sms * 16) blocks = sms * 16;
@@ -969,7 +969,7 @@ cudaError_t launch_nb_finish_split(const double* crd_ro, const int* natoms, cons
         launch_force(A, grid, st);
     }
     IntArgs I{ps, param_id, vel, crd_ro, crd_out, fed, rnd, nullptr, temp, t0, 1, 1, sp.dt, sp.gamma, sp.tautp, sp.scaled};
-    finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb);
+    finish_unmarked_kernel<<<count, kThreads, 0, st>>>(I, mark, dirty, fnb, e_nb, bump, bump_by);
     if (np > 0) {
         const int grid = count < 4 * sms ? count : 4 * sms;
         finish_marked_kernel<<<grid, kThreads, 0, st>>>(I, list, cnt, dirty, fnb, epart, e_nb);
