@@ -826,6 +826,9 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
                              int variant, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
+    // a few thousand tetrads do not fill the machine either way: then the shorter per-warp critical path of the
+    // one-tetrad kernel wins (1,000 tetrads: 17 vs 30 us); beyond that the two-tetrad kernel's throughput does
+    if (variant == 0) variant = count < 4096 ? 1 : 2;
     if (variant == 1) superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
     else              superpose2_kernel<<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
     return cudaGetLastError();

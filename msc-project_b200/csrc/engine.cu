@@ -154,7 +154,7 @@ struct edmd_engine {
     long calls = 0;
 
     int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
-    int sup_variant = 0; // superposition kernel: 0 two tetrads per warp, 1 one tetrad per warp (EDMD_SUPERPOSE=1)
+    int sup_variant = 0; // superposition kernel: 0 by size, 1 one tetrad per warp, 2 two tetrads per warp (EDMD_SUPERPOSE)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
     bool use_graph = true, graph_valid = false;
@@ -585,7 +585,7 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
         e->sp.mole_least = p->mole_Least;
     }
     // tuning switches for A/B measurements (none changes a result bit)
-    if (const char* v = getenv("EDMD_SUPERPOSE")) e->sup_variant = atoi(v) == 1 ? 1 : 0;
+    if (const char* v = getenv("EDMD_SUPERPOSE")) { const int k = atoi(v); if (k >= 0 && k <= 2) e->sup_variant = k; }
     if (const char* v = getenv("EDMD_RNG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 16) e->rng_ctas_per_sm = k; }
     if (const char* v = getenv("EDMD_RNG_BRANCH")) e->rng_branch = atoi(v) != 0;
     *out = e;

@@ -14,7 +14,7 @@ inline double nb_effective_cut2(const SimParams& sp) {
 }
 
 constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scratch (ed.cu)
-// variant: 0 = two tetrads per warp (default), 1 = one tetrad per warp with the coordinates staged in shared memory
+// variant: 0 = by size, 1 = one tetrad per warp with the coordinates staged in shared memory, 2 = two tetrads per warp
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
                              int variant, cudaStream_t st);
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
