@@ -14,10 +14,12 @@
 //    produced 32 atoms at a time by the whole warp into a shared tile, then lane k runs the
 //    k-th running sum as a chain of DADDs.  The sums that depend only on the parameter set
 //    (centroid and norm of the average structure) are computed once at upload.  This file is
-//    compiled with -fmad=false, so every expression rounds exactly like the CPU build and R and the
-//    centroids are BIT-IDENTICAL to the reference's (the offset vector, which only translates the
-//    tetrad, is a fixed-order tree sum: ~1 ulp).  Bound by the latency of 2 x 252 dependent adds
-//    per tetrad, hidden by the independent warps of an SM.
+//    compiled with -fmad=false, so every expression rounds exactly like the CPU build and R,
+//    centroids and offset are BIT-IDENTICAL to the reference's.  Latency-bound (3 x 252
+//    dependent adds per tetrad) and hidden by the independent warps of an SM.  (The offset vector as a
+//    tree sum — it only translates the tetrad — was tried: 0.10 ms faster at 1e5 tetrads, but the 1-ulp
+//    shift of a tetrad's coordinates (1e-14 A instead of 1e-17) is amplified by the cancellation in
+//    clashing electrostatic contacts to 4e-10 on NB forces: over the parity bound, dropped.)
 //
 //  ed_project_warp_kernel (parameter sets with <= 12 eigenvectors: one warp per tetrad, the set's
 //    eigenvectors staged in shared memory once per run of tetrads) and ed_project_kernel (any
@@ -31,6 +33,7 @@
 //    24 KB of state.
 #include "common.cuh"
 #include "kernels.h"
+#include "bounds.cuh"
 
 namespace edmd {
 
@@ -303,32 +306,25 @@ __global__ void __launch_bounds__(32 * kSupWarps, 6) superpose_kernel(SupArgs A)
         qcp_rotation(R, m, (g_ref + g_x) * 0.5);
     }
 
-    // Offset vector, edmd.cpp:97-102: mean over atoms of avg_i - R x_i on the UNCENTRED arrays (re-read,
-    // L2-resident).  Unlike the rotation, which is amplified ~100x into d = R x_c - avg_c, this vector only
-    // translates the whole tetrad: a last-bit difference in it is a last-bit difference of the coordinates and
-    // cancels in the next step's centring.  It is therefore summed per lane and then with a fixed butterfly
-    // (bit-stable, ~1 ulp from the sequential sum) instead of with a third 252-step chain.
-    double off = 0.0;
-    {
+    double off = 0.0;   // offset-vector terms on the UNCENTRED arrays (re-read, L2-resident), edmd.cpp:97-101
+    for (int b = 0; b < na; b += 32) {
+        const int i = b + lane;
         double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-        for (int b = 0; b < na; b += 32) {
-            const int i = b + lane;
-            const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
-            if (i + 32 < na) {
-                pa0 = AV[i + 32]; pa1 = AV[S + i + 32]; pa2 = AV[2 * S + i + 32];
-                px0 = X[i + 32]; px1 = X[S + i + 32]; px2 = X[2 * S + i + 32];
-            }
-            if (i < na) {
-                w0 = w0 + (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
-                w1 = w1 + (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
-                w2 = w2 + (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
-            }
+        const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
+        if (i + 32 < na) {
+            pa0 = AV[i + 32]; pa1 = AV[S + i + 32]; pa2 = AV[2 * S + i + 32];
+            px0 = X[i + 32]; px1 = X[S + i + 32]; px2 = X[2 * S + i + 32];
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            w0 = w0 + __shfl_xor_sync(full, w0, o); w1 = w1 + __shfl_xor_sync(full, w1, o); w2 = w2 + __shfl_xor_sync(full, w2, o);
+        if (i < na) {
+            w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
+            w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
+            w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
         }
-        off = lane == 0 ? w0 : lane == 1 ? w1 : w2;
+        sm.tile[0][lane] = w0; sm.tile[1][lane] = w1; sm.tile[2][lane] = w2;
+        __syncwarp();
+        const int cnt = na - b < 32 ? na - b : 32;
+        if (lane < 3) off = tile_chain(off, sm.tile[lane], cnt);
+        __syncwarp();
     }
 
     double* out = A.sup + (size_t)t * kSupWords;
@@ -367,7 +363,7 @@ __device__ __forceinline__ double tile_chain16(double s, const double* row, int 
     return s;
 }
 
-__global__ void __launch_bounds__(32 * kS2Warps, 7) superpose2_kernel(SupArgs A) {
+__global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A) {
     __shared__ Sup2Tile tiles[kS2Warps];
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -446,8 +442,7 @@ __global__ void __launch_bounds__(32 * kS2Warps, 7) superpose2_kernel(SupArgs A)
         qcp_rotation(R, m, (g_ref + g_x) * 0.5);
     }
 
-    // pass 3 — offset vector on the UNCENTRED arrays, edmd.cpp:97-102: per-lane sums, then a fixed butterfly over
-    // the half-warp (see superpose_kernel for why this sum need not be sequential)
+    // pass 3 — offset-vector terms on the UNCENTRED arrays, edmd.cpp:97-101
     double off = 0.0;
     {
         double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0, px0 = 0.0, px1 = 0.0, px2 = 0.0;
@@ -455,7 +450,6 @@ __global__ void __launch_bounds__(32 * kS2Warps, 7) superpose2_kernel(SupArgs A)
             pa0 = AV[hl]; pa1 = AV[S + hl]; pa2 = AV[2 * S + hl];
             px0 = X[hl]; px1 = X[S + hl]; px2 = X[2 * S + hl];
         }
-        double w0 = 0.0, w1 = 0.0, w2 = 0.0;
         for (int b = 0; b < na_max; b += 16) {
             const int i = b + hl;
             const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
@@ -463,17 +457,18 @@ __global__ void __launch_bounds__(32 * kS2Warps, 7) superpose2_kernel(SupArgs A)
                 pa0 = AV[i + 16]; pa1 = AV[S + i + 16]; pa2 = AV[2 * S + i + 16];
                 px0 = X[i + 16]; px1 = X[S + i + 16]; px2 = X[2 * S + i + 16];
             }
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
             if (i < na) {
-                w0 = w0 + (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
-                w1 = w1 + (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
-                w2 = w2 + (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
+                w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
+                w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
+                w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
             }
+            tile[0][hl] = w0; tile[1][hl] = w1; tile[2][hl] = w2;
+            __syncwarp();
+            const int cnt = na - b < 16 ? na - b : 16;
+            if (hl < 3 && cnt > 0) off = tile_chain16(off, tile[hl], cnt);
+            __syncwarp();
         }
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {       // xor offsets below 16 stay inside the half-warp
-            w0 = w0 + __shfl_xor_sync(full, w0, o); w1 = w1 + __shfl_xor_sync(full, w1, o); w2 = w2 + __shfl_xor_sync(full, w2, o);
-        }
-        off = hl == 0 ? w0 : hl == 1 ? w1 : w2;
     }
 
     if (!live) return;
@@ -546,6 +541,11 @@ struct EdArgs {
     const int* order;    // [count] tetrads of this launch sorted by parameter set
     int count;
     int chunk;           // tetrads per CTA
+    // epilogue of the warp-per-tetrad kernel: bounding spheres of the re-embedded tetrad for the culled distance
+    // pass (nb.cu), while its coordinates are still in L1/L2; gb == nullptr: none
+    double* gb;
+    const int* perm;     // [P][kMaxStride] slot -> atom
+    int n_total;         // tetrads in the system (layout of gb)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
@@ -822,6 +822,10 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
                     F[2 * S + a] = R[2] * f0 + R[5] * f1 + R[8] * f2;
                 }
             }
+            if (A.gb) {
+                __syncwarp();   // the lanes read each other's freshly stored coordinates (slot order != atom order)
+                group_bounds_tetrad(X, A.perm + (size_t)ps * kMaxStride, A.gb, A.n_total, t, S, lane);
+            }
             e = e_next; t = t_next;
         }
         if (lane == 0 && e < e1) atomicMin(&sNext, e);   // first tetrad of the next set seen by this warp
@@ -845,7 +849,9 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
 
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                              bool use_warp_kernel, cudaStream_t st) {
+                              bool use_warp_kernel, double* gb, const int* perm, int n_total, bool* gb_done,
+                              cudaStream_t st) {
+    if (gb_done) *gb_done = false;
     if (count <= 0) return cudaSuccess;
     cudaError_t err;
     if (use_warp_kernel && ps.NEV <= kNevReg) {
@@ -866,15 +872,16 @@ cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const do
         }
         int chunk = (count + 2 * sms - 1) / (2 * sms);   // two resident CTAs per SM, one wave
         if (chunk < kWarps) chunk = kWarps;              // at least one tetrad per warp
-        EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
+        EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk, gb, perm, n_total};
         if (ps.S == kMaxStride) ed_project_warp_kernel<kMaxStride><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
         else                    ed_project_warp_kernel<0><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
+        if (gb_done) *gb_done = gb != nullptr;
         return cudaGetLastError();
     }
     int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer
     if (chunk < 1) chunk = 1;
     if (chunk > 8) chunk = 8;
-    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
+    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk, nullptr, nullptr, 0};
     ed_project_kernel<<<(count + chunk - 1) / chunk, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }

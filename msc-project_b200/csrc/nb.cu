@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "step_math.cuh"
+#include "bounds.cuh"
 
 namespace edmd {
 
@@ -286,53 +287,15 @@ cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, un
     return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd, const int* natoms, const int* param_id,
-                                                            const int* perm, double* gb, int n, int S,
-                                                            const unsigned char* need) {
-    const unsigned full = 0xffffffffu;
+__global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd, const int* param_id, const int* perm,
+                                                            double* gb, int n, int S, const unsigned char* need,
+                                                            int skip0, int skip1) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
     if (!need[t]) return;        // not an end of any pair in this engine's scan slice (sharded runs)
-    const double* X = crd + (size_t)t * 3 * S;
-    const int* PM = perm + (size_t)param_id[t] * kMaxStride;
-    int a[8];
-#pragma unroll
-    for (int g = 0; g < 8; g++) a[g] = PM[32 * g + lane];     // slot -> atom, -1 = empty slot
-    double gx = 0.0, gy = 0.0, gz = 0.0, gr = -1.0;            // lane g keeps group g's sphere
-#pragma unroll
-    for (int g = 0; g < 8; g++) {
-        const bool on = a[g] >= 0;
-        const double x = on ? X[a[g]] : 0.0, y = on ? X[S + a[g]] : 0.0, z = on ? X[2 * S + a[g]] : 0.0;
-        const double cx = __shfl_sync(full, x, 0), cy = __shfl_sync(full, y, 0), cz = __shfl_sync(full, z, 0);
-        const bool any = __shfl_sync(full, (int)on, 0) != 0;   // slots fill from 0: empty slot 0 = empty group
-        const double d2 = on ? (x - cx) * (x - cx) + (y - cy) * (y - cy) + (z - cz) * (z - cz) : 0.0;
-        float f = __double2float_ru(d2);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) f = fmaxf(f, __shfl_xor_sync(full, f, o));
-        const double rad = any ? (double)__fsqrt_ru(f) * (1.0 + 1e-12) + 1e-12 : -1.0;
-        if (lane == 0) *reinterpret_cast<double4*>(gb + ((size_t)t * 8 + g) * 4) = make_double4(cx, cy, cz, rad);
-        if (lane == g) { gx = cx; gy = cy; gz = cz; gr = rad; }
-    }
-    // tetrad sphere: centre = mean of the non-empty group centres, radius = max over groups of
-    // (distance to the centre + group radius); lanes 0..7 hold the groups
-    const bool have = lane < 8 && gr >= 0.0;
-    double tx = have ? gx : 0.0, ty = have ? gy : 0.0, tz = have ? gz : 0.0; int tn = have ? 1 : 0;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        tx += __shfl_xor_sync(full, tx, o); ty += __shfl_xor_sync(full, ty, o);
-        tz += __shfl_xor_sync(full, tz, o); tn += __shfl_xor_sync(full, tn, o);
-    }
-    // (every lane runs the shuffles below: tn is non-zero in lanes 0..7 only, and a shuffle inside a
-    // branch that part of the named lanes skip is undefined)
-    const double inv = tn > 0 ? (double)__frcp_rn((float)tn) : 0.0;   // any centre will do: the radius is measured from it
-    tx *= inv; ty *= inv; tz *= inv;
-    const double dd = (gx - tx) * (gx - tx) + (gy - ty) * (gy - ty) + (gz - tz) * (gz - tz);
-    float reach = have ? __fadd_ru(__fsqrt_ru(__double2float_ru(dd)), __double2float_ru(gr)) : 0.0f;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) reach = fmaxf(reach, __shfl_xor_sync(full, reach, o));
-    const double trad = tn > 0 ? (double)reach * (1.0 + 1e-12) + 1e-12 : -1.0;
-    if (lane == 0) *reinterpret_cast<double4*>(gb + (size_t)n * 32 + (size_t)t * 4) = make_double4(tx, ty, tz, trad);
+    if (t >= skip0 && t < skip1) return;   // spheres already produced by the ED projection's epilogue
+    group_bounds_tetrad(crd + (size_t)t * 3 * S, perm + (size_t)param_id[t] * kMaxStride, gb, n, t, S, lane);
 }
 
 // One thread per listed pair: whole-tetrad spheres first (one test instead of 64 for the typical
@@ -507,7 +470,8 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* work, unsigned* count, const int* param_id, const int* perm,
-                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st) {
+                                const unsigned char* need, int skip0, int skip1, unsigned long long* const* peers, int world,
+                                cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
@@ -515,7 +479,9 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     }
     // work buffer: one CullItem per listed pair at most; the item counter was zeroed by the caller
     CullItem* items = reinterpret_cast<CullItem*>(work);
-    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, natoms, param_id, perm, gb, n, S, need);
+    // tetrads [skip0, skip1) already carry current spheres (engine.cu: gb_fresh); all of them: no launch at all
+    if (!(skip0 <= 0 && skip1 >= n))
+        group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need, skip0, skip1);
     const long long want = p1 - p0;
     pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
     // The number of selected pairs is only known on the device: a fixed grid of up to 128 single-warp
