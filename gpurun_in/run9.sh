@@ -1,0 +1,5 @@
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2_t9.log 2>&1; tail -4 gpurun_out/r2_t9.log
+echo fused; timeout 200 python tools/dist_perf.py 100000 50 1 2>&1 | tail -1
+echo separate; EDMD_FUSE_BOUNDS=0 timeout 200 python tools/dist_perf.py 100000 50 1 2>&1 | tail -1
+echo fused12500; timeout 100 python tools/dist_perf.py 12500 100 1 2>&1 | tail -1
+echo coil; timeout 100 python tools/dist_perf.py 10000 50 0 coil 2 40 2>&1 | tail -1
