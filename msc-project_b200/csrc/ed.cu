@@ -33,7 +33,6 @@
 //    24 KB of state.
 #include "common.cuh"
 #include "kernels.h"
-#include "bounds.cuh"
 
 namespace edmd {
 
@@ -541,11 +540,6 @@ struct EdArgs {
     const int* order;    // [count] tetrads of this launch sorted by parameter set
     int count;
     int chunk;           // tetrads per CTA
-    // epilogue of the warp-per-tetrad kernel: bounding spheres of the re-embedded tetrad for the culled distance
-    // pass (nb.cu), while its coordinates are still in L1/L2; gb == nullptr: none
-    double* gb;
-    const int* perm;     // [P][kMaxStride] slot -> atom
-    int n_total;         // tetrads in the system (layout of gb)
 };
 
 __global__ void __launch_bounds__(kThreads, 2) ed_project_kernel(EdArgs A) {
@@ -822,10 +816,9 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
                     F[2 * S + a] = R[2] * f0 + R[5] * f1 + R[8] * f2;
                 }
             }
-            if (A.gb) {
-                __syncwarp();   // the lanes read each other's freshly stored coordinates (slot order != atom order)
-                group_bounds_tetrad(X, A.perm + (size_t)ps * kMaxStride, A.gb, A.n_total, t, S, lane);
-            }
+            // (Writing the distance pass's bounding spheres here, while the coordinates are in L1/L2, was tried:
+            // the epilogue cost 0.18 ms at 1e5 tetrads — what the separate group_bounds_kernel costs — because this
+            // kernel runs 16 warps per SM and the sphere code is a chain of dependent loads.  Dropped.)
             e = e_next; t = t_next;
         }
         if (lane == 0 && e < e1) atomicMin(&sNext, e);   // first tetrad of the next set seen by this warp
@@ -849,9 +842,7 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
 
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                              bool use_warp_kernel, double* gb, const int* perm, int n_total, bool* gb_done,
-                              cudaStream_t st) {
-    if (gb_done) *gb_done = false;
+                              bool use_warp_kernel, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     cudaError_t err;
     if (use_warp_kernel && ps.NEV <= kNevReg) {
@@ -872,16 +863,15 @@ cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const do
         }
         int chunk = (count + 2 * sms - 1) / (2 * sms);   // two resident CTAs per SM, one wave
         if (chunk < kWarps) chunk = kWarps;              // at least one tetrad per warp
-        EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk, gb, perm, n_total};
+        EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
         if (ps.S == kMaxStride) ed_project_warp_kernel<kMaxStride><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
         else                    ed_project_warp_kernel<0><<<(count + chunk - 1) / chunk, kThreads, smem, st>>>(A);
-        if (gb_done) *gb_done = gb != nullptr;
         return cudaGetLastError();
     }
     int chunk = count / (sms * 8);          // keep >= 8 CTAs per SM before making runs longer
     if (chunk < 1) chunk = 1;
     if (chunk > 8) chunk = 8;
-    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk, nullptr, nullptr, 0};
+    EdArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, t0, scaled, order, count, chunk};
     ed_project_kernel<<<(count + chunk - 1) / chunk, kThreads, 0, st>>>(A);
     return cudaGetLastError();
 }

@@ -85,8 +85,6 @@ struct edmd_engine {
     unsigned char* d_dirty = nullptr; // [n] fnb of this tetrad is non-zero from an earlier step
     double* d_epart = nullptr;        // [n][8][2] pair energies per slot group (force pass -> finish kernel)
     double* d_gb = nullptr;                 // [n][8][4] group + [n][4] tetrad bounding spheres (scan mode 4)
-    bool gb_fresh = false;                  // d_gb holds the spheres of the CURRENT e->crd for all owned tetrads (written
-                                            // by the ED projection's epilogue); cleared by whatever changes e->crd
     int* d_perm = nullptr;                  // [P][kMaxStride] slot -> atom, compact groups of 32 (culling scan, force pass)
     unsigned long long* d_grp = nullptr;    // [P][32] atom -> slot group, byte c of entry l = group of atom 32c+l
     unsigned long long* d_pmask = nullptr;  // counter + [pairs_cap] {pair index, 8x8 group mask} work items (scan mode 4)
@@ -156,7 +154,6 @@ struct edmd_engine {
     long calls = 0;
 
     int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
-    bool fuse_bounds = true;   // bounding spheres in the projection epilogue (EDMD_FUSE_BOUNDS=0: separate pass)
     int sup_variant = 0; // superposition kernel: 0 by size, 1 one tetrad per warp, 2 two tetrads per warp (EDMD_SUPERPOSE)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
@@ -402,7 +399,6 @@ int upload_order(edmd_engine* e) {
 // be reading crd).  The ED pass consumes them from there; every other consumer calls this first.
 int normalize(edmd_engine* e) {
     if (!e->latest_in_crd2) return 0;
-    e->gb_fresh = false;
     const size_t off = (size_t)e->t0 * 3 * e->S, cnt = (size_t)(e->t1 - e->t0) * 3 * e->S;
     if (cnt) CK(cudaMemcpyAsync(e->crd + off, e->crd2 + off, sizeof(double) * cnt, cudaMemcpyDeviceToDevice, e->st));
     e->latest_in_crd2 = false;
@@ -419,9 +415,8 @@ int do_ed(edmd_engine* e) {
     timer_begin(e, T_SUP);
     CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->st));
     timer_end(e, T_SUP, 0);
-    const bool want_gb = e->scan_mode == 4 && e->fuse_bounds;
     CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
-                         e->t1 - e->t0, e->sp.scaled, warp, want_gb ? e->d_gb : nullptr, e->d_perm, e->n, &e->gb_fresh, e->st));
+                         e->t1 - e->t0, e->sp.scaled, warp, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -444,7 +439,6 @@ int do_scan(edmd_engine* e) {
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
                                e->d_gb, e->d_pmask, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->d_param_id, e->d_perm, e->d_need,
-                               e->gb_fresh ? e->t0 : 0, e->gb_fresh ? e->t1 : 0,
                                e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -549,7 +543,6 @@ int stage_out(edmd_engine* e, const double* planes, int slot) {
 }
 int stage_in(edmd_engine* e, double* planes, int slot) {
     if (int rc = snap_fence(e)) return rc;
-    if (planes == e->crd) e->gb_fresh = false;
     double* d = e->d_stage + (size_t)slot * e->total3;
     CK(cudaMemcpyAsync(d, e->h_stage + (size_t)slot * e->total3, sizeof(double) * e->total3,
                        cudaMemcpyHostToDevice, e->st));
@@ -595,7 +588,6 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
     if (const char* v = getenv("EDMD_SUPERPOSE")) { const int k = atoi(v); if (k >= 0 && k <= 2) e->sup_variant = k; }
     if (const char* v = getenv("EDMD_RNG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 16) e->rng_ctas_per_sm = k; }
     if (const char* v = getenv("EDMD_RNG_BRANCH")) e->rng_branch = atoi(v) != 0;
-    if (const char* v = getenv("EDMD_FUSE_BOUNDS")) e->fuse_bounds = atoi(v) != 0;
     *out = e;
     return 0;
 }

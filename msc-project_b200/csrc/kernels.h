@@ -17,12 +17,9 @@ constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scrat
 // variant: 0 = by size, 1 = one tetrad per warp with the coordinates staged in shared memory, 2 = two tetrads per warp
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
                              int variant, cudaStream_t st);
-// gb / perm / n_total: when gb is given and the warp-per-tetrad kernel runs, its epilogue also writes the bounding
-// spheres of the culled distance pass for the tetrads it processed; *gb_done tells whether it did
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
-                              bool use_warp_kernel, double* gb, const int* perm, int n_total, bool* gb_done,
-                              cudaStream_t st);
+                              bool use_warp_kernel, cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                            long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
@@ -31,8 +28,7 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* items, unsigned* item_count, const int* param_id, const int* perm,
-                                const unsigned char* need, int skip0, int skip1 /* tetrads whose spheres are current */,
-                                unsigned long long* const* peers, int world, cudaStream_t st);
+                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st);
 cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
 // hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the

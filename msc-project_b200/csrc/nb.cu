@@ -288,13 +288,11 @@ cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, un
 }
 
 __global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd, const int* param_id, const int* perm,
-                                                            double* gb, int n, int S, const unsigned char* need,
-                                                            int skip0, int skip1) {
+                                                            double* gb, int n, int S, const unsigned char* need) {
     const int lane = threadIdx.x & 31;
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= n) return;
     if (!need[t]) return;        // not an end of any pair in this engine's scan slice (sharded runs)
-    if (t >= skip0 && t < skip1) return;   // spheres already produced by the ED projection's epilogue
     group_bounds_tetrad(crd + (size_t)t * 3 * S, perm + (size_t)param_id[t] * kMaxStride, gb, n, t, S, lane);
 }
 
@@ -470,8 +468,7 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* work, unsigned* count, const int* param_id, const int* perm,
-                                const unsigned char* need, int skip0, int skip1, unsigned long long* const* peers, int world,
-                                cudaStream_t st) {
+                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
@@ -479,9 +476,7 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     }
     // work buffer: one CullItem per listed pair at most; the item counter was zeroed by the caller
     CullItem* items = reinterpret_cast<CullItem*>(work);
-    // tetrads [skip0, skip1) already carry current spheres (engine.cu: gb_fresh); all of them: no launch at all
-    if (!(skip0 <= 0 && skip1 >= n))
-        group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need, skip0, skip1);
+    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need);
     const long long want = p1 - p0;
     pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
     // The number of selected pairs is only known on the device: a fixed grid of up to 128 single-warp
