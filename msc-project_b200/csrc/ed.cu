@@ -362,6 +362,11 @@ __device__ __forceinline__ double tile_chain16(double s, const double* row, int 
     return s;
 }
 
+// Instruction count is what bounds this kernel (ncu: 67 % of the issue slots, FP64 pipe 30 %), so the loops are
+// written for it: the atom stride is a template constant when it is the usual 256 (the three planes of a block
+// are then one address plus immediates), the prefetch index is clamped instead of guarded, and tile entries of
+// atoms beyond the tetrad's count are left as they come — the chains never read them.
+template <int SC>
 __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A) {
     __shared__ Sup2Tile tiles[kS2Warps];
     const unsigned full = 0xffffffffu;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     const int e = (blockIdx.x * kS2Warps + warp) * 2 + half;
     const bool live = e < A.count;                       // the last warp may carry a single tetrad
     double (*tile)[kS2Row] = tiles[warp].v[half];
-    const int S = A.ps.S;
+    const int S = SC ? SC : A.ps.S;
     const int t = A.t0 + (live ? e : A.count - 1);       // (a dead half reads a valid tetrad and writes nothing)
     const int ps = A.param_id[t];
     const int na = live ? A.ps.na[ps] : 0;
@@ -379,21 +384,20 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
     const double* PRE = A.ps.pre + 4 * (size_t)ps;
     const double ca0 = PRE[0], ca1 = PRE[1], ca2 = PRE[2], g_ref = PRE[3];
+    const int last = S - 1;                              // prefetches past the tetrad read its zero padding
 
     // pass 1 — CenterCoords, qcprot.c:370-379: sums in atom order, then divide by len
     double cx0, cx1, cx2;
     {
         double acc = 0.0;
-        double p0 = 0.0, p1 = 0.0, p2 = 0.0;
-        if (hl < na) { p0 = X[hl]; p1 = X[S + hl]; p2 = X[2 * S + hl]; }
+        double p0 = X[hl], p1 = X[S + hl], p2 = X[2 * S + hl];
         for (int b = 0; b < na_max; b += 16) {
-            const int i = b + hl;
-            const double x0 = p0, x1 = p1, x2 = p2;
-            if (i + 16 < na) { p0 = X[i + 16]; p1 = X[S + i + 16]; p2 = X[2 * S + i + 16]; }
-            tile[0][hl] = x0; tile[1][hl] = x1; tile[2][hl] = x2;
+            tile[0][hl] = p0; tile[1][hl] = p1; tile[2][hl] = p2;
+            const int nx = min(b + 16 + hl, last);
+            p0 = X[nx]; p1 = X[S + nx]; p2 = X[2 * S + nx];
             __syncwarp();
-            const int cnt = na - b < 16 ? na - b : 16;
-            if (hl < 3 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt);
+            const int cnt = na - b;
+            if (hl < 3 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt < 16 ? cnt : 16);
             __syncwarp();
         }
         const double c = na > 0 ? acc / na : 0.0;
@@ -404,34 +408,21 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     double R[9];
     {
         double acc = 0.0;
-        double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0, px0 = 0.0, px1 = 0.0, px2 = 0.0;
-        if (hl < na) {
-            pa0 = AV[hl]; pa1 = AV[S + hl]; pa2 = AV[2 * S + hl];
-            px0 = X[hl]; px1 = X[S + hl]; px2 = X[2 * S + hl];
-        }
+        double pa0 = AV[hl], pa1 = AV[S + hl], pa2 = AV[2 * S + hl];
+        double px0 = X[hl], px1 = X[S + hl], px2 = X[2 * S + hl];
         for (int b = 0; b < na_max; b += 16) {
-            const int i = b + hl;
-            const double r0 = pa0, r1 = pa1, r2 = pa2, y0 = px0, y1 = px1, y2 = px2;
-            if (i + 16 < na) {
-                pa0 = AV[i + 16]; pa1 = AV[S + i + 16]; pa2 = AV[2 * S + i + 16];
-                px0 = X[i + 16]; px1 = X[S + i + 16]; px2 = X[2 * S + i + 16];
-            }
-            double v[10];
-#pragma unroll
-            for (int k = 0; k < 10; k++) v[k] = 0.0;
-            if (i < na) {
-                const double a0 = r0 - ca0, a1 = r1 - ca1, a2 = r2 - ca2;
-                const double x0 = y0 - cx0, x1 = y1 - cx1, x2 = y2 - cx2;     // centred copies, qcprot.c:382-386
-                v[0] = a0 * x0; v[1] = a0 * x1; v[2] = a0 * x2;
-                v[3] = a1 * x0; v[4] = a1 * x1; v[5] = a1 * x2;
-                v[6] = a2 * x0; v[7] = a2 * x1; v[8] = a2 * x2;
-                v[9] = (x0 * x0 + x1 * x1) + x2 * x2;
-            }
-#pragma unroll
-            for (int k = 0; k < 10; k++) tile[k][hl] = v[k];
+            const double a0 = pa0 - ca0, a1 = pa1 - ca1, a2 = pa2 - ca2;
+            const double x0 = px0 - cx0, x1 = px1 - cx1, x2 = px2 - cx2;      // centred copies, qcprot.c:382-386
+            const int nx = min(b + 16 + hl, last);
+            pa0 = AV[nx]; pa1 = AV[S + nx]; pa2 = AV[2 * S + nx];
+            px0 = X[nx]; px1 = X[S + nx]; px2 = X[2 * S + nx];
+            tile[0][hl] = a0 * x0; tile[1][hl] = a0 * x1; tile[2][hl] = a0 * x2;
+            tile[3][hl] = a1 * x0; tile[4][hl] = a1 * x1; tile[5][hl] = a1 * x2;
+            tile[6][hl] = a2 * x0; tile[7][hl] = a2 * x1; tile[8][hl] = a2 * x2;
+            tile[9][hl] = (x0 * x0 + x1 * x1) + x2 * x2;
             __syncwarp();
-            const int cnt = na - b < 16 ? na - b : 16;
-            if (hl < 10 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt);
+            const int cnt = na - b;
+            if (hl < 10 && cnt > 0) acc = tile_chain16(acc, tile[hl], cnt < 16 ? cnt : 16);
             __syncwarp();
         }
         double m[9];
@@ -444,28 +435,18 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     // pass 3 — offset-vector terms on the UNCENTRED arrays, edmd.cpp:97-101
     double off = 0.0;
     {
-        double pa0 = 0.0, pa1 = 0.0, pa2 = 0.0, px0 = 0.0, px1 = 0.0, px2 = 0.0;
-        if (hl < na) {
-            pa0 = AV[hl]; pa1 = AV[S + hl]; pa2 = AV[2 * S + hl];
-            px0 = X[hl]; px1 = X[S + hl]; px2 = X[2 * S + hl];
-        }
+        double pa0 = AV[hl], pa1 = AV[S + hl], pa2 = AV[2 * S + hl];
+        double px0 = X[hl], px1 = X[S + hl], px2 = X[2 * S + hl];
         for (int b = 0; b < na_max; b += 16) {
-            const int i = b + hl;
-            const double a0 = pa0, a1 = pa1, a2 = pa2, x0 = px0, x1 = px1, x2 = px2;
-            if (i + 16 < na) {
-                pa0 = AV[i + 16]; pa1 = AV[S + i + 16]; pa2 = AV[2 * S + i + 16];
-                px0 = X[i + 16]; px1 = X[S + i + 16]; px2 = X[2 * S + i + 16];
-            }
-            double w0 = 0.0, w1 = 0.0, w2 = 0.0;
-            if (i < na) {
-                w0 = (a0 - (R[0] * x0 + R[1] * x1 + R[2] * x2));
-                w1 = (a1 - (R[3] * x0 + R[4] * x1 + R[5] * x2));
-                w2 = (a2 - (R[6] * x0 + R[7] * x1 + R[8] * x2));
-            }
-            tile[0][hl] = w0; tile[1][hl] = w1; tile[2][hl] = w2;
+            tile[0][hl] = (pa0 - (R[0] * px0 + R[1] * px1 + R[2] * px2));
+            tile[1][hl] = (pa1 - (R[3] * px0 + R[4] * px1 + R[5] * px2));
+            tile[2][hl] = (pa2 - (R[6] * px0 + R[7] * px1 + R[8] * px2));
+            const int nx = min(b + 16 + hl, last);
+            pa0 = AV[nx]; pa1 = AV[S + nx]; pa2 = AV[2 * S + nx];
+            px0 = X[nx]; px1 = X[S + nx]; px2 = X[2 * S + nx];
             __syncwarp();
-            const int cnt = na - b < 16 ? na - b : 16;
-            if (hl < 3 && cnt > 0) off = tile_chain16(off, tile[hl], cnt);
+            const int cnt = na - b;
+            if (hl < 3 && cnt > 0) off = tile_chain16(off, tile[hl], cnt < 16 ? cnt : 16);
             __syncwarp();
         }
     }
@@ -836,7 +817,8 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
     // one-tetrad kernel wins (1,000 tetrads: 17 vs 30 us); beyond that the two-tetrad kernel's throughput does
     if (variant == 0) variant = count < 4096 ? 1 : 2;
     if (variant == 1) superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
-    else              superpose2_kernel<<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
+    else if (ps.S == kMaxStride) superpose2_kernel<kMaxStride><<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
+    else                         superpose2_kernel<0><<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
     return cudaGetLastError();
 }
 

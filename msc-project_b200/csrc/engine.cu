@@ -813,7 +813,7 @@ int edmd_upload_tetrads(edmd_engine* e, const edmd_tetrad* tets, int n, const in
     CK(cudaMemcpyAsync(e->d_chg, chg.data(), sizeof(double) * chg.size(), cudaMemcpyHostToDevice, e->st));
     CK(cudaMemcpyAsync(e->d_eval, eval.data(), sizeof(double) * eval.size(), cudaMemcpyHostToDevice, e->st));
     CK(cudaMemcpyAsync(e->d_evec, evec.data(), sizeof(double) * evec.size(), cudaMemcpyHostToDevice, e->st));
-    for (double* buf : {e->vel, e->fed, e->rnd, e->fnb})
+    for (double* buf : {e->vel, e->fed, e->rnd, e->fnb, e->crd2})     // (padding slots beyond a tetrad's atoms stay zero)
         CK(cudaMemsetAsync(buf, 0, sizeof(double) * planes, e->st));
     CK(cudaMemsetAsync(e->obs, 0, sizeof(double) * 4 * n, e->st));
     CK(cudaStreamSynchronize(e->st));   // host vectors go out of scope
