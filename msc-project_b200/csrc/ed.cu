@@ -379,7 +379,9 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     const int t = A.t0 + (live ? e : A.count - 1);       // (a dead half reads a valid tetrad and writes nothing)
     const int ps = A.param_id[t];
     const int na = live ? A.ps.na[ps] : 0;
-    const int na_max = max(na, __shfl_xor_sync(full, na, 16));   // both halves walk the same number of blocks
+    // both halves walk the same number of blocks (redux.sync: the result is in a uniform register, so the block
+    // loops branch on a provably warp-uniform value and their __syncwarp()s cost nothing extra)
+    const int na_max = __reduce_max_sync(full, na);
     const double* X = A.crd + (size_t)t * 3 * S;
     const double* AV = A.ps.avg + (size_t)ps * 3 * S;
     const double* PRE = A.ps.pre + 4 * (size_t)ps;
@@ -688,7 +690,10 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
     const int S = SC ? SC : A.ps.S;
     double* sEV = wsm;               // [kNevReg][3][S]
     double* sAV = wsm + kNevReg * 3 * S;   // [3][S]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp-uniform values pass through redux.sync (result in a uniform register): the compiler then sees the
+    // loops over tetrads as warp-uniform and drops the reconvergence code around every shuffle in them
+    const int warp = __reduce_max_sync(0xffffffffu, tid >> 5);
     const int e0 = blockIdx.x * A.chunk;
     const int e1 = (e0 + A.chunk < A.count) ? e0 + A.chunk : A.count;
     const int nk = S >> 5;
@@ -696,8 +701,8 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
 
     int base = e0;
     while (base < e1) {
-        const int ps = A.param_id[A.order[base]];
-        const int na = A.ps.na[ps], nev = A.ps.nev[ps];
+        const int ps = __reduce_max_sync(0xffffffffu, A.param_id[A.order[base]]);
+        const int na = __reduce_max_sync(0xffffffffu, A.ps.na[ps]), nev = __reduce_max_sync(0xffffffffu, A.ps.nev[ps]);
         if (tid == 0) sNext = e1;
         {   // stage the set's tables (rows j >= NEV are zero; the arrays are zero-padded beyond na / nev)
             const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
@@ -711,11 +716,11 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
         if (my_idx >= 0 && my_idx < nev) el = A.ps.eval[(size_t)ps * A.ps.NEV + my_idx];
 
         int e = base + warp;
-        int t = e < e1 ? A.order[e] : -1;
+        int t = __reduce_max_sync(0xffffffffu, e < e1 ? A.order[e] : -1);
         while (e < e1) {
-            if (A.param_id[t] != ps) break;
+            if (__reduce_max_sync(0xffffffffu, A.param_id[t]) != ps) break;
             const int e_next = e + kWarps;
-            const int t_next = e_next < e1 ? A.order[e_next] : -1;
+            const int t_next = __reduce_max_sync(0xffffffffu, e_next < e1 ? A.order[e_next] : -1);
             const double* XIN = A.crd_in + (size_t)t * 3 * S;
             const double* SUP = A.sup + (size_t)t * kSupWords;
             double x[8][3];
@@ -804,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
         }
         if (lane == 0 && e < e1) atomicMin(&sNext, e);   // first tetrad of the next set seen by this warp
         __syncthreads();
-        base = sNext;
+        base = __reduce_max_sync(0xffffffffu, sNext);
         __syncthreads();
     }
 }

@@ -744,13 +744,13 @@ __global__ void __launch_bounds__(32 * kForceWarps, 5) nb_force_kernel(AccArgs A
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
     const int S = A.S;
-    const unsigned items = 8u * (A.count ? *A.count : (unsigned)A.count_host);
+    // (warp-uniform values pass through redux.sync, whose result lives in a uniform register: the loops below
+    // then branch on provably uniform values and the ballots and shuffles in them need no reconvergence code)
+    const unsigned items = 8u * __reduce_max_sync(full, A.count ? *A.count : (unsigned)A.count_host);
     for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(A.ticket, 1u);
-        item = __shfl_sync(full, item, 0);
+        const unsigned item = __reduce_max_sync(full, lane == 0 ? atomicAdd(A.ticket, 1u) : 0u);
         if (item >= items) return;
-        const int t = A.list ? A.list[item >> 3] : A.t0 + (int)(item >> 3);
+        const int t = __reduce_max_sync(full, A.list ? A.list[item >> 3] : A.t0 + (int)(item >> 3));
         const int w = (int)(item & 7u);                          // my slot group
         const int ps = A.param_id[t];
         const int a = A.perm[(size_t)ps * kMaxStride + 32 * w + lane];   // my atom
@@ -765,9 +765,10 @@ __global__ void __launch_bounds__(32 * kForceWarps, 5) nb_force_kernel(AccArgs A
         double F0 = 0.0, F1 = 0.0, F2 = 0.0;   // tetrad totals, pair-list order
         double E0 = 0.0, E1 = 0.0;             // this lane's share of the pair energies
 
-        const long long e_begin = A.adj_off[t], e_end = A.adj_off[t + 1];
-        for (long long base = e_begin; base < e_end; base += 32) {
-            const long long e = base + lane;
+        // (adjacency offsets fit 32 bits: the builder limits the list to 2^30 pairs)
+        const int e_begin = __reduce_max_sync(full, (int)A.adj_off[t]), e_end = __reduce_max_sync(full, (int)A.adj_off[t + 1]);
+        for (int base = e_begin; base < e_end; base += 32) {
+            const int e = base + lane;
             unsigned pmv = 0; int code = 0;
             if (e < e_end) {
                 const unsigned long long m = A.hit[A.adj_pair[e]];
@@ -782,8 +783,8 @@ __global__ void __launch_bounds__(32 * kForceWarps, 5) nb_force_kernel(AccArgs A
             while (todo) {
                 const int b = __ffs(todo) - 1;
                 todo &= todo - 1;
-                const int u = __shfl_sync(full, code, b) & 0x7fffffff;
-                const unsigned pm = __shfl_sync(full, pmv, b);
+                const int u = __reduce_max_sync(full, lane == b ? (code & 0x7fffffff) : 0);
+                const unsigned pm = __reduce_max_sync(full, lane == b ? pmv : 0u);
                 acc_partner<HAS_Q>(A, sm, wslot, lane, u, pm, xi, yi, zi, qi, F0, F1, F2, E0, E1);
             }
         }

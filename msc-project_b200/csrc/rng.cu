@@ -43,6 +43,18 @@ __device__ __forceinline__ double div_rand_max(double x) {
     return __fma_rn(r, c, q0);
 }
 
+// 16807^i mod (2^31 - 1), i = 0..30.  srand() fills r[i] = 16807 * r[i-1] mod (2^31-1) by Schrage's method
+// (stdlib/random_r.c: hi = w / 127773, lo = w % 127773, w = 16807*lo - 2836*hi, +2^31-1 if negative), which is the
+// exact modular product — also for a negative (int32) seed with C's truncating division — so r[i] is the closed
+// form kSeedPow[i] * (int32)seed mod (2^31-1) and every lane gets its word without the 30-step serial loop.
+// (Equality with the iteration checked for edge seeds 0, 1, 2^31-1, 2^31, 2^32-1 and 20,000 random ones:
+// tests/test_oracle.py::test_glibc_seed_closed_form.)
+__constant__ unsigned kSeedPow[31] = {
+    1u, 16807u, 282475249u, 1622650073u, 984943658u, 1144108930u, 470211272u, 101027544u, 1457850878u, 1458777923u,
+    2007237709u, 823564440u, 1115438165u, 1784484492u, 74243042u, 114807987u, 1137522503u, 1441282327u, 16531729u,
+    823378840u, 143542612u, 896544303u, 1474833169u, 1264817709u, 1998097157u, 1817129560u, 1131570933u, 197493099u,
+    1404280278u, 893351816u, 1505795335u};
+
 struct RngArgs {
     ParamSets ps;
     const double* noise; // [P][3][S] sqrt(2*gamma*kT*m/dt), launch_noise_table
@@ -60,12 +72,15 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
     const int lane = threadIdx.x & 31;
     // warps walk the tetrads with a grid stride: a full grid gives one tetrad per warp; the step's side branch
     // launches a small resident grid instead, which leaves most of every SM to the kernels it runs beside
+    // (warp index and normal count pass through redux.sync, whose result lives in a uniform register: the loops
+    // below then branch on provably warp-uniform values and the shuffles in them need no reconvergence code)
     const int warps = gridDim.x * (blockDim.x >> 5);
-    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < A.count; w += warps) {
+    const int w0 = __reduce_max_sync(0xffffffffu, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    for (int w = w0; w < A.count; w += warps) {
     const int t = A.t0 + w;
     const int ps = A.param_id[t];
     const int S = A.ps.S;
-    const int n3 = 3 * A.ps.na[ps];
+    const int n3 = __reduce_max_sync(0xffffffffu, 3 * A.ps.na[ps]);
     const double* NZ = A.noise + (size_t)ps * 3 * S;
     double* out = A.rnd + (size_t)t * 3 * S;
 
@@ -76,15 +91,13 @@ __global__ void __launch_bounds__(128) random_terms_kernel(RngArgs A) {
     unsigned seed = (unsigned)((long)(rs + (unsigned)(A.rank * A.rank * A.rank)) + A.time0);
     if (seed == 0) seed = 1;
 
-    // srand(): r[0] = seed, r[i] = 16807 * r[i-1] mod 2147483647 (Schrage), i = 1..30
+    // srand(): r[0] = seed, r[i] = 16807 * r[i-1] mod 2147483647 (Schrage), i = 1..30 — closed form, see kSeedPow
     const int want = (lane + 3) % 31;   // lane l keeps r[(l+3) % 31]
-    int word = (int)seed;
-    unsigned P = (want == 0) ? seed : 0u;
-    for (int i = 1; i < 31; i++) {
-        const int hi = word / 127773, lo = word % 127773;
-        word = 16807 * lo - 2836 * hi;
-        if (word < 0) word += 2147483647;
-        if (i == want) P = (unsigned)word;
+    unsigned P = seed;
+    if (want != 0) {
+        long long rem = ((long long)kSeedPow[want] * (long long)(int)seed) % 2147483647LL;   // sign of the dividend
+        if (rem < 0) rem += 2147483647LL;
+        P = (unsigned)rem;
     }
     for (int b = 0; b < 10; b++) P = lfg_next_block(P, lane);   // 310 discarded outputs
 

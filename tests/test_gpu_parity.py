@@ -176,3 +176,15 @@ def test_gc90_shipped_config_block(edmd, po, gc90):
     (co, vo), (cg, vg) = o.get_state(), g.get_state()
     assert rel(cg, co) < TOL and rel(vg, vo) < TOL
     assert np.allclose(g.energies(), o.energies(), rtol=1e-10)
+
+
+@pytest.mark.parametrize("target", [0, 1, 2 ** 31 - 1, 2 ** 31, 2 ** 31 + 5, 2 ** 32 - 1])
+def test_random_terms_edge_seeds(edmd, po, target):
+    """srand() edge cases: seed 0 (glibc substitutes 1), 2^31-1 (every seed word 0), and seeds whose int32 view is
+    negative (C's truncating division in the seeding recurrence) — the kernel's closed-form seeding must give the
+    reference stream for all of them."""
+    s = edmd.make_gc90().subset(range(4))
+    time0 = target - 13580                      # first call: seed = (unsigned)(13579 + rank^3 + time0), rank 1
+    o = po.Oracle(s, "port"); o.set_time(time0); o.set_rng_calls(0); o.random_terms(rank=1)
+    g = edmd.Engine(s); g.random_terms(mode=1, time0=time0, rank=1, calls_before=0)
+    assert np.array_equal(g.get_forces()["rnd"], o.get_forces()["rnd"])

@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STRIDE = 7
 T0 = 1000000000
 
@@ -181,3 +182,48 @@ def test_division_free_rand_max_quotient_is_exact(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
     assert int(out[0]) == 0          # corrected form: no mismatch
     assert int(out[1]) > 0           # (the plain product alone is NOT exact - the correction matters)
+
+
+def test_glibc_seed_closed_form(po):
+    """rng.cu seeds every lane with 16807^i * (int32)seed mod (2^31-1) instead of iterating srand()'s Schrage
+    recurrence: the kernel's table and the closed form must reproduce the words stdlib/random_r.c's seeding loop
+    (restated here with C's truncating division and int32 range checks) produces, for edge and random seeds."""
+    M = 2147483647
+    table = [pow(16807, i, M) for i in range(31)]
+    src = open(os.path.join(ROOT, "msc-project_b200", "csrc", "rng.cu")).read()
+    body = src[src.index("kSeedPow[31] = {") + len("kSeedPow[31] = {"):]
+    body = body[:body.index("}")]
+    assert [int(x.strip().rstrip("u")) for x in body.split(",")] == table
+
+    def cdiv(a, b):
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+
+    def iterate(seed):
+        seed = seed or 1
+        w = seed if seed < 2 ** 31 else seed - 2 ** 32
+        out = [seed]
+        for _ in range(30):
+            hi = cdiv(w, 127773); lo = w - hi * 127773
+            w = 16807 * lo - 2836 * hi
+            assert -2 ** 31 <= w < 2 ** 31
+            if w < 0:
+                w += M
+            out.append(w)
+        return out
+
+    def closed(seed):
+        seed = seed or 1
+        s = seed if seed < 2 ** 31 else seed - 2 ** 32
+        out = [seed]
+        for i in range(1, 31):
+            p = table[i] * s
+            rem = abs(p) % M
+            rem = -rem if p < 0 else rem
+            out.append(rem + M if rem < 0 else rem)
+        return out
+
+    rng = np.random.default_rng(3)
+    seeds = [0, 1, 2, M - 1, M, M + 1, 2 ** 31, 2 ** 31 + 5, 2 ** 32 - 2, 2 ** 32 - 1, 1000013580] + [int(x) for x in rng.integers(0, 2 ** 32, 20000)]
+    for sd in seeds:
+        assert iterate(sd) == closed(sd), sd
