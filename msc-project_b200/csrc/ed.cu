@@ -822,8 +822,13 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
     // one-tetrad kernel wins (1,000 tetrads: 17 vs 30 us); beyond that the two-tetrad kernel's throughput does
     if (variant == 0) variant = count < 4096 ? 1 : 2;
     if (variant == 1) superpose_kernel<<<(count + kSupWarps - 1) / kSupWarps, 32 * kSupWarps, 0, st>>>(B);
-    else if (ps.S == kMaxStride) superpose2_kernel<kMaxStride><<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
-    else                         superpose2_kernel<0><<<(count + 2 * kS2Warps - 1) / (2 * kS2Warps), 32 * kS2Warps, 0, st>>>(B);
+    else {
+        // (fewer CTAs per SM — tried by padding the CTA with unused shared memory — is monotonically slower:
+        // 1.15 / 1.16 / 1.20 / 1.21 / 1.31 ms of ED at 8 / 7 / 6 / 5 / 4 CTAs per SM: the kernel lives on occupancy)
+        const int grid = (count + 2 * kS2Warps - 1) / (2 * kS2Warps);
+        if (ps.S == kMaxStride) superpose2_kernel<kMaxStride><<<grid, 32 * kS2Warps, 0, st>>>(B);
+        else                    superpose2_kernel<0><<<grid, 32 * kS2Warps, 0, st>>>(B);
+    }
     return cudaGetLastError();
 }
 
