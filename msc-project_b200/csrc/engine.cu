@@ -154,6 +154,7 @@ struct edmd_engine {
     long calls = 0;
 
     int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
+    int cull_dense_min = 9;   // sphere masks with this many blocks or more go to the tiled distance kernel (EDMD_CULL_DENSE)
     int sup_variant = 0; // superposition kernel: 0 by size, 1 one tetrad per warp, 2 two tetrads per warp (EDMD_SUPERPOSE)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
     // CUDA graph of one step (edmd_step replays it; rebuilt whenever anything it bakes in changes)
@@ -438,7 +439,8 @@ int do_scan(edmd_engine* e) {
         if (int rc = ensure_need(e)) return rc;
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
-                               e->d_gb, e->d_pmask, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->d_param_id, e->d_perm, e->d_need,
+                               e->d_gb, e->d_pmask, e->pmask_cap, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->cull_dense_min,
+                               e->d_param_id, e->d_perm, e->d_need,
                                e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -588,6 +590,7 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
     if (const char* v = getenv("EDMD_SUPERPOSE")) { const int k = atoi(v); if (k >= 0 && k <= 2) e->sup_variant = k; }
     if (const char* v = getenv("EDMD_RNG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 16) e->rng_ctas_per_sm = k; }
     if (const char* v = getenv("EDMD_RNG_BRANCH")) e->rng_branch = atoi(v) != 0;
+    if (const char* v = getenv("EDMD_CULL_DENSE")) { const int k = atoi(v); if (k >= 0 && k <= 65) e->cull_dense_min = k; }
     *out = e;
     return 0;
 }
@@ -1593,13 +1596,15 @@ int edmd_nb_stats_ex(edmd_engine* e, long long out[5]) {
     }
     for (int t = e->t0; t < e->t1; t++) out[1] += marked[t];
     if (e->scan_mode == 4 && e->d_pmask) {
-        unsigned cnt = 0;
-        CK(cudaMemcpy(&cnt, e->d_mark + e->n + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
-        out[3] = cnt;
+        unsigned cnt[2] = {0, 0};   // sparse-mask items from the front of the work buffer, dense-mask items from its back
+        CK(cudaMemcpy(cnt, e->d_mark + e->n + 2, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost));
+        out[3] = (long long)cnt[0] + cnt[1];
         // work items {pair index, sphere mask} (nb.cu: CullItem)
-        std::vector<unsigned long long> items(2 * (size_t)cnt);
-        if (cnt) CK(cudaMemcpy(items.data(), e->d_pmask, sizeof(unsigned long long) * items.size(), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < cnt; i++) out[4] += __builtin_popcountll(items[2 * i + 1]);
+        std::vector<unsigned long long> items(2 * (size_t)std::max(cnt[0], cnt[1]));
+        if (cnt[0]) CK(cudaMemcpy(items.data(), e->d_pmask, sizeof(unsigned long long) * 2 * cnt[0], cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt[0]; i++) out[4] += __builtin_popcountll(items[2 * i + 1]);
+        if (cnt[1]) CK(cudaMemcpy(items.data(), e->d_pmask + 2 * ((size_t)e->pmask_cap - cnt[1]), sizeof(unsigned long long) * 2 * cnt[1], cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt[1]; i++) out[4] += __builtin_popcountll(items[2 * i + 1]);
     }
     return 0;
 }

@@ -27,8 +27,9 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* items, unsigned* item_count, const int* param_id, const int* perm,
-                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st);
+                                unsigned long long* items, long long items_cap, unsigned* item_counts /* [2] */,
+                                int dense_min, const int* param_id, const int* perm, const unsigned char* need,
+                                unsigned long long* const* peers, int world, cudaStream_t st);
 cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
 
 // hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the

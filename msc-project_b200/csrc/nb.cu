@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd
 struct CullItem { long long k; unsigned long long mask; };
 
 __global__ void __launch_bounds__(128) pair_select_kernel(const double* gb, const int2* pairs, long long p0, long long p1,
-                                                          double dcut, CullItem* items, unsigned* count, int n) {
+                                                          double dcut, CullItem* items, CullItem* items_back, unsigned* count,
+                                                          int dense_min, int n) {
     const long long k = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long m = 0;
     if (k < p1) {
@@ -332,18 +333,30 @@ __global__ void __launch_bounds__(128) pair_select_kernel(const double* gb, cons
             }
         }
     }
-    const unsigned live = __ballot_sync(0xffffffffu, m != 0ull);
-    if (!live) return;
+    // sparse masks go to the front list (count[0], ascending from items), dense ones to the back list (count[1],
+    // descending from items_back): one buffer of one item per listed pair serves both
     const int lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == __ffs(live) - 1) base = atomicAdd(count, (unsigned)__popc(live));
-    base = __shfl_sync(0xffffffffu, base, __ffs(live) - 1);
-    if (m) items[base + __popc(live & ((1u << lane) - 1u))] = CullItem{k, m};
+    const bool dense = m != 0ull && __popcll(m) >= dense_min;
+    const unsigned live = __ballot_sync(0xffffffffu, m != 0ull && !dense);
+    const unsigned lived = __ballot_sync(0xffffffffu, dense);
+    if (live) {
+        unsigned base = 0;
+        if (lane == __ffs(live) - 1) base = atomicAdd(count, (unsigned)__popc(live));
+        base = __shfl_sync(0xffffffffu, base, __ffs(live) - 1);
+        if (m && !dense) items[base + __popc(live & ((1u << lane) - 1u))] = CullItem{k, m};
+    }
+    if (lived) {
+        unsigned base = 0;
+        if (lane == __ffs(lived) - 1) base = atomicAdd(count + 1, (unsigned)__popc(lived));
+        base = __shfl_sync(0xffffffffu, base, __ffs(lived) - 1);
+        if (dense) *(items_back - (long long)(base + __popc(lived & ((1u << lane) - 1u)))) = CullItem{k, m};
+    }
 }
 
-__global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs A, const CullItem* items,
+__global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs A, const CullItem* items_back,
                                                                                     const unsigned* count,
                                                                                     const int* param_id, const int* perm) {
+    // items_back: the dense-mask list, item i at items_back[-i] (pair_select_kernel)
     constexpr double kBias = 16384.0;
     __shared__ __align__(16) double sb[4][kMaxStride + 2];
     __shared__ __align__(128) double raw[3 * kMaxStride];
@@ -371,7 +384,7 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
     const unsigned i0 = (unsigned)(blk * chunk);
     const unsigned i1 = (i0 + chunk < total) ? i0 + chunk : total;
     CullItem mine{0, 0ull};
-    if (i0 + lane < i1) mine = items[i0 + lane];
+    if (i0 + lane < i1) mine = *(items_back - (long long)(i0 + lane));
     const int nitems = (int)(i1 - i0);
     int it = 0;
     long long k = __shfl_sync(0xffffffffu, mine.k, 0);
@@ -465,27 +478,114 @@ __global__ void __launch_bounds__(kScanThreads, 15) nb_scan_cull_kernel(ScanArgs
     }   // blocks of the work list
 }
 
+// Light-weight variant of the masked distance kernel for SPARSE masks (the usual case: 2-3 of a pair's 64 blocks
+// survive the sphere tests).  nb_scan_cull_kernel above keeps a whole tetrad in an 8-atom register tile and
+// pulls the whole partner by TMA — 122 registers, 14 KB of shared memory, 15 warps per SM — and spends ~9 us per
+// item on latencies it cannot overlap, whatever the number of blocks.  Here one warp takes one item and walks its
+// set bits; a lane holds ONE atom of the current group of the lower-numbered tetrad, the 32 atoms of the partner
+// group are gathered through the slot table into a 1 KB shared strip and read as broadcasts: ~40 registers, so
+// the SM holds 48 warps and the per-item latency is hidden by other items.  Same Gram arithmetic, same
+// conservative threshold, same refined mask; dense masks (dense_min or more blocks per pair) still go to the tiled
+// kernel, which amortises the partner loads over eight groups (pair_select_kernel files the items in two lists).
+constexpr int kBlkWarps = 4;
+
+__global__ void __launch_bounds__(32 * kBlkWarps, 12) nb_scan_blocks_kernel(ScanArgs A, const CullItem* items,
+                                                                            const unsigned* count,
+                                                                            const int* param_id, const int* perm) {
+    constexpr double kBias = 16384.0;
+    __shared__ __align__(16) double4 sp[kBlkWarps][32];      // partner group: x', y', z', |x'|^2 + B
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wslot = threadIdx.x >> 5;
+    const int S = A.S;
+    const unsigned total = __reduce_max_sync(full, *count);
+    const unsigned w0 = __reduce_max_sync(full, blockIdx.x * kBlkWarps + wslot);
+    for (unsigned item = w0; item < total; item += gridDim.x * kBlkWarps) {
+        const CullItem it = items[item];
+        const unsigned mlo = __reduce_max_sync(full, (unsigned)it.mask), mhi = __reduce_max_sync(full, (unsigned)(it.mask >> 32));
+        const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+        const int k = (int)__reduce_max_sync(full, (unsigned)it.k);
+        const int2 pr = A.pairs[k];
+        const int tr = __reduce_min_sync(full, pr.x < pr.y ? pr.x : pr.y), ts = __reduce_max_sync(full, pr.x < pr.y ? pr.y : pr.x);
+        const double* Xr = A.crd + (size_t)tr * 3 * S;
+        const double* Xs = A.crd + (size_t)ts * 3 * S;
+        const int* PR = perm + (size_t)param_id[tr] * kMaxStride;
+        const int* PS = perm + (size_t)param_id[ts] * kMaxStride;
+        const double ox = Xr[0], oy = Xr[S], oz = Xr[2 * S];   // pair-local origin, as in the tiled kernel
+        unsigned long long refined = 0ull;
+        bool wild = false;
+#pragma unroll 1
+        for (int r = 0; r < 8; r++) {
+            const unsigned mr = column_bits(m, r);             // partner groups that may reach my group r
+            if (!mr) continue;
+            const int a = PR[32 * r + lane];
+            double xi = 0.0, yi = 0.0, zi = 0.0; int hthr = -1;
+            if (a >= 0) {
+                const double lx = Xr[a] - ox, ly = Xr[S + a] - oy, lz = Xr[2 * S + a] - oz;
+                xi = -2.0 * lx; yi = -2.0 * ly; zi = -2.0 * lz;
+                const double w = fma(lz, lz, fma(ly, ly, lx * lx));
+                wild = wild || !(w < 0.99 * kBias);
+                hthr = hi_word((A.cut + kBias) - w) + 1;
+            }
+            unsigned todo = mr;
+            while (todo) {
+                const int g = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int b = PS[32 * g + lane];
+                double4 v = make_double4(0.0, 0.0, 0.0, 1e300);   // an empty slot never hits
+                if (b >= 0) {
+                    const double lx = Xs[b] - ox, ly = Xs[S + b] - oy, lz = Xs[2 * S + b] - oz;
+                    v = make_double4(lx, ly, lz, fma(lz, lz, fma(ly, ly, lx * lx)) + kBias);
+                }
+                sp[wslot][lane] = v;
+                __syncwarp();
+                int mm = 0x7fffffff;
+#pragma unroll 8
+                for (int j = 0; j < 32; j++) {
+                    const double4 q = sp[wslot][j];
+                    mm = min(mm, hi_word(fma(xi, q.x, fma(yi, q.y, fma(zi, q.z, q.w)))));
+                }
+                if (__any_sync(full, mm <= hthr)) refined |= 1ull << (8 * g + r);
+                __syncwarp();
+            }
+        }
+        // a tetrad too spread out for the bias: keep every block the sphere tests let through
+        if (__any_sync(full, wild)) refined = m;
+        if (refined) publish_hit(A, k, lane, refined);
+    }
+}
+
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
-                                unsigned long long* work, unsigned* count, const int* param_id, const int* perm,
-                                const unsigned char* need, unsigned long long* const* peers, int world, cudaStream_t st) {
+                                unsigned long long* work, long long work_items, unsigned* count, int dense_min,
+                                const int* param_id, const int* perm, const unsigned char* need,
+                                unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
         cudaError_t err = cudaMemsetAsync(hit + p0, 0, sizeof(unsigned long long) * (size_t)(p1 - p0), st);
         if (err != cudaSuccess) return err;
     }
-    // work buffer: one CullItem per listed pair at most; the item counter was zeroed by the caller
+    // work buffer: one CullItem per listed pair at most; the two item counters were zeroed by the caller
     CullItem* items = reinterpret_cast<CullItem*>(work);
+    CullItem* items_back = items + (work_items - 1);
     group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need);
     const long long want = p1 - p0;
-    pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, count, n);
-    // The number of selected pairs is only known on the device: a fixed grid of up to 128 single-warp
-    // CTAs per SM walks the blocks of the list; CTAs beyond the list read the counter and exit.
+    pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, items_back, count,
+                                                                     dense_min, n);
+    // The number of selected pairs is only known on the device: fixed grids walk the lists; CTAs beyond a list
+    // read its counter and exit.  pair_select_kernel files an item by the population of its sphere mask: sparse
+    // masks (< dense_min blocks) at the front of the work buffer for the light-weight block kernel, dense ones at the
+    // back for the tiled kernel (count[0] / count[1]; the two lists grow towards each other).
     const long long blocks_wanted = (long long)sms * 64;
-    const int grid = (int)(want < 2 * blocks_wanted ? want : 2 * blocks_wanted);
     long long bits; memcpy(&bits, &cut2_eff, 8);
     ScanArgs A{crd, natoms, pairs, hit, p0, p1, S, (int)(bits >> 32), (int)blocks_wanted, cut2_eff, peers, world};
-    nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, items, count, param_id, perm);
+    if (dense_min > 1) {          // (dense_min <= 1: every item is "dense", tiled kernel only)
+        const long long warps = want < 48LL * sms ? want : 48LL * sms;
+        nb_scan_blocks_kernel<<<(int)((warps + kBlkWarps - 1) / kBlkWarps), 32 * kBlkWarps, 0, st>>>(A, items, count, param_id, perm);
+    }
+    if (dense_min <= 64) {        // (dense_min > 64: no mask is dense, block kernel only)
+        const int grid = (int)(want < 2 * blocks_wanted ? want : 2 * blocks_wanted);
+        nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, items_back, count + 1, param_id, perm);
+    }
     return cudaGetLastError();
 }
 
