@@ -39,6 +39,12 @@ namespace edmd {
 
 __device__ __forceinline__ int hi_word(double v) { return __double2hiint(v); }
 
+// bits g of the result = bits 8g + r of m, g = 0..7 (one multiply gathers the eight strided bits:
+// bit 8g' times 2^(56-7g) lands on bit 56+g only for g' = g, and no two products collide)
+__device__ __forceinline__ unsigned column_bits(unsigned long long m, int r) {
+    return (unsigned)((((m >> r) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+
 struct ScanArgs {
     const double* crd;      // [n][3][S]
     const int* natoms;      // [n] atoms per tetrad
@@ -774,12 +780,6 @@ struct AccArgs {
 struct ForceSmem {
     double px[kForceWarps][kAccBuf], py[kForceWarps][kAccBuf], pz[kForceWarps][kAccBuf], pq[kForceWarps][kAccBuf];
 };
-
-// bits g of the result = bits 8g + r of m, g = 0..7 (one multiply gathers the eight strided bits:
-// bit 8g' times 2^(56-7g) lands on bit 56+g only for g' = g, and no two products collide)
-__device__ __forceinline__ unsigned column_bits(unsigned long long m, int r) {
-    return (unsigned)((((m >> r) & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
-}
 
 template <bool HAS_Q>
 __device__ __forceinline__ void acc_partner(const AccArgs& A, ForceSmem& sm, int w, int lane, int u, unsigned pm,
