@@ -446,12 +446,15 @@ def main():
     barrier()
     st = g.nb_stats()
 
-    # ---- the reference's outer loop (simulation.cpp:34-55): ntsync = 100 steps, merge, pair-list rebuild
-    barrier()
-    t0 = time.perf_counter()
-    run_steps(100); sh.merge(); sh.build_pairlist(); g.sync()
-    barrier()
-    block_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    # ---- the reference's outer loop (simulation.cpp:34-55): ntsync = 100 steps, merge, pair-list rebuild; the second of
+    # two blocks is timed (the first pays one-off costs: lazily loaded kernels, first peer copies, graph re-instantiation)
+    block_ms = None
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        run_steps(100); sh.merge(); sh.build_pairlist(); g.sync()
+        barrier()
+        block_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
     # ---- e2e: through the C ABI with HOST buffers, one step per call.  One GPU: edmd_step_host on the caller's
     # pinned Tetrad arrays (upload -> step -> download).  Several GPUs: every rank moves its OWN block of tetrads
