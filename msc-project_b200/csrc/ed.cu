@@ -372,10 +372,14 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int half = lane >> 4, hl = lane & 15, base = lane & 16;
-    const int e = (blockIdx.x * kS2Warps + warp) * 2 + half;
-    const bool live = e < A.count;                       // the last warp may carry a single tetrad
     double (*tile)[kS2Row] = tiles[warp].v[half];
     const int S = SC ? SC : A.ps.S;
+    // warps walk the tetrad pairs with a grid stride; the launcher sizes the grid so that every warp gets the same
+    // number of pairs (+-1) instead of leaving a thin second wave on a few SMs
+    const int units = (A.count + 1) >> 1, stride = gridDim.x * kS2Warps;
+    for (int unit = __reduce_max_sync(full, blockIdx.x * kS2Warps + warp); unit < units; unit += stride) {
+    const int e = unit * 2 + half;
+    const bool live = e < A.count;                       // the last pair may hold a single tetrad
     const int t = A.t0 + (live ? e : A.count - 1);       // (a dead half reads a valid tetrad and writes nothing)
     const int ps = A.param_id[t];
     const int na = live ? A.ps.na[ps] : 0;
@@ -453,15 +457,17 @@ __global__ void __launch_bounds__(32 * kS2Warps, 8) superpose2_kernel(SupArgs A)
         }
     }
 
-    if (!live) return;
-    double* out = A.sup + (size_t)t * kSupWords;
+    if (live) {
+        double* out = A.sup + (size_t)t * kSupWords;
 #pragma unroll
-    for (int j = 0; j < 9; j++) if (hl == j) out[j] = R[j];
-    if (hl < 3) {
-        out[9 + hl] = off / na;                                              // edmd.cpp:102
-        out[12 + hl] = hl == 0 ? ca0 : hl == 1 ? ca1 : ca2;
-        out[15 + hl] = hl == 0 ? cx0 : hl == 1 ? cx1 : cx2;
+        for (int j = 0; j < 9; j++) if (hl == j) out[j] = R[j];
+        if (hl < 3) {
+            out[9 + hl] = off / na;                                              // edmd.cpp:102
+            out[12 + hl] = hl == 0 ? ca0 : hl == 1 ? ca1 : ca2;
+            out[15 + hl] = hl == 0 ? cx0 : hl == 1 ? cx1 : cx2;
+        }
     }
+    }   // tetrad pairs of this warp
 }
 
 // Sum 12 per-lane values over the warp with a halving butterfly: at each of the 5 stages a lane
@@ -814,8 +820,17 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
     }
 }
 
+// Grid for a kernel whose warps walk `units` work units with a grid stride: every warp gets ceil(units / slots)
+// units or one less, where slots = the warps the machine holds at once — no thin last wave.
+static int balanced_ctas(int units, int warps_per_cta, int sms, int warps_per_sm) {
+    const long long slots = (long long)sms * warps_per_sm;
+    const long long per_warp = (units + slots - 1) / slots;
+    const long long warps = per_warp > 0 ? (units + per_warp - 1) / per_warp : 1;
+    return (int)((warps + warps_per_cta - 1) / warps_per_cta);
+}
+
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
-                             int variant, cudaStream_t st) {
+                             int variant, int sms, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
     SupArgs B{ps, param_id, crd_in, sup, t0, count};
     // a few thousand tetrads do not fill the machine either way: then the shorter per-warp critical path of the
@@ -825,7 +840,7 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
     else {
         // (fewer CTAs per SM — tried by padding the CTA with unused shared memory — is monotonically slower:
         // 1.15 / 1.16 / 1.20 / 1.21 / 1.31 ms of ED at 8 / 7 / 6 / 5 / 4 CTAs per SM: the kernel lives on occupancy)
-        const int grid = (count + 2 * kS2Warps - 1) / (2 * kS2Warps);
+        const int grid = balanced_ctas((count + 1) / 2, kS2Warps, sms, 8 * kS2Warps);
         if (ps.S == kMaxStride) superpose2_kernel<kMaxStride><<<grid, 32 * kS2Warps, 0, st>>>(B);
         else                    superpose2_kernel<0><<<grid, 32 * kS2Warps, 0, st>>>(B);
     }

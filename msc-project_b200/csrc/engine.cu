@@ -170,6 +170,7 @@ struct edmd_engine {
     long long launches = 0;
     long long graph_launches = 0;   // kernel launches inside one replay of the step graph
     unsigned char* d_need = nullptr; bool need_valid = false;   // [n] tetrad is an end of a pair in [p0,p1) (scan mode 4)
+    int* d_need_list = nullptr; int need_count = 0;             // the same tetrads as a compact list (+ its device counter)
     double* d_pspre = nullptr;              // [P][4] per-set superposition constants (ed.cu)
     double* d_noise = nullptr; bool noise_valid = false;   // [P][3][S] Langevin noise amplitudes
     cudaStream_t st_copy = nullptr;                 // edmd_step_host: velocity upload beside the ED / scan kernels
@@ -239,6 +240,7 @@ void free_system(edmd_engine* e) {
     cudaFree(e->d_noise); e->d_noise = nullptr; e->noise_valid = false;
     cudaFree(e->d_pspre); e->d_pspre = nullptr;
     cudaFree(e->d_need); e->d_need = nullptr; e->need_valid = false;
+    cudaFree(e->d_need_list); e->d_need_list = nullptr; e->need_count = 0;
     cudaFree(e->d_order); e->d_order = nullptr;
     cudaFree(e->d_cell); cudaFree(e->d_cell_sorted); cudaFree(e->d_tet); cudaFree(e->d_tet_sorted);
     cudaFree(e->d_partners); cudaFree(e->d_partners_sorted); cudaFree(e->d_cub_tmp);
@@ -414,7 +416,7 @@ int do_ed(edmd_engine* e) {
     // share it: worth it when sets are shared (replicated DNA), not when every tetrad has its own.
     const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && (long long)e->n >= 8LL * e->P);
     timer_begin(e, T_SUP);
-    CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->st));
+    CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->sms, e->st));
     timer_end(e, T_SUP, 0);
     CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
                          e->t1 - e->t0, e->sp.scaled, warp, e->st));
@@ -424,9 +426,15 @@ int do_ed(edmd_engine* e) {
 // which tetrads the culled distance pass needs bounding spheres for: the ends of this engine's pairs
 int ensure_need(edmd_engine* e) {
     if (e->need_valid) return 0;
-    if (!e->d_need) CK(dev_alloc(&e->d_need, (size_t)e->n));
-    CK(launch_mark_needed(e->d_pairs, e->p0, e->p1, e->d_need, e->n, e->st));
-    e->launches++;
+    if (!e->d_need) {
+        CK(dev_alloc(&e->d_need, (size_t)e->n)); CK(dev_alloc(&e->d_need_list, (size_t)e->n + 1));
+    }
+    int* cnt = e->d_need_list + e->n;
+    CK(launch_mark_needed(e->d_pairs, e->p0, e->p1, e->d_need, e->d_need_list, cnt, e->n, e->st));
+    e->need_count = 0;
+    if (e->p1 > e->p0) CK(cudaMemcpyAsync(&e->need_count, cnt, sizeof(int), cudaMemcpyDeviceToHost, e->st));
+    CK(cudaStreamSynchronize(e->st));
+    e->launches += 2;
     e->need_valid = true;
     return 0;
 }
@@ -440,7 +448,7 @@ int do_scan(edmd_engine* e) {
         timer_begin(e, T_SCAN);
         CK(launch_nb_scan_cull(e->crd, e->d_natoms, e->d_pairs, cur_hits(e), e->p0, e->p1, e->n, e->S, cut_eff, e->sms,
                                e->d_gb, e->d_pmask, e->pmask_cap, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->cull_dense_min,
-                               e->d_param_id, e->d_perm, e->d_need,
+                               e->d_param_id, e->d_perm, e->d_need_list, e->need_count,
                                e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
         timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
         e->hits_valid = true;
@@ -513,7 +521,7 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before,
     // beside other kernels: a resident grid of rng_ctas_per_sm CTAs per SM, so that the generator takes a fixed
     // slice of every SM for most of the step instead of the whole machine for a part of it
     CK(launch_random_terms(e->ps, e->d_noise, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
-                           calls_before + e->t0, calls_dev, side ? e->sms * e->rng_ctas_per_sm : 0, on));
+                           calls_before + e->t0, calls_dev, side ? e->sms * e->rng_ctas_per_sm : -e->sms, on));
     if (!side) timer_end(e, T_RNG, 1); else e->launches++;
     e->rnd_zero = false;
     return 0;

@@ -16,7 +16,7 @@ inline double nb_effective_cut2(const SimParams& sp) {
 constexpr int kSupWordsHost = 24;   // doubles per tetrad of superposition scratch (ed.cu)
 // variant: 0 = by size, 1 = one tetrad per warp with the coordinates staged in shared memory, 2 = two tetrads per warp
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
-                             int variant, cudaStream_t st);
+                             int variant, int sms, cudaStream_t st);
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                               bool use_warp_kernel, cudaStream_t st);
@@ -28,9 +28,10 @@ cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pai
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* items, long long items_cap, unsigned* item_counts /* [2] */,
-                                int dense_min, const int* param_id, const int* perm, const unsigned char* need,
+                                int dense_min, const int* param_id, const int* perm, const int* need_list, int need_count,
                                 unsigned long long* const* peers, int world, cudaStream_t st);
-cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st);
+cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int* list, int* count,
+                               int n, cudaStream_t st);
 
 // hit: per-pair 8 x 8 block masks written by the distance pass (0 = pair not flagged); perm / grp: the
 // per-parameter-set slot -> atom and atom -> slot-group tables the masks refer to (engine.cu); epart: [n][8][2]
@@ -93,7 +94,7 @@ cudaError_t build_halo_list(const int2* pairs, long long np, long long p0, long 
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                const long* calls_dev, int max_ctas /* 0: one tetrad per warp */, cudaStream_t st);
+                                const long* calls_dev, int max_ctas /* 0: one tetrad per warp; > 0: at most that many CTAs; -sms: balanced */, cudaStream_t st);
 cudaError_t launch_ps_precompute(const ParamSets& ps, int P, double* pre, cudaStream_t st);
 cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const SimParams& sp, cudaStream_t st);
 cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st);

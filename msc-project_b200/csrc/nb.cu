@@ -286,19 +286,28 @@ __global__ void mark_needed_kernel(const int2* pairs, long long p0, long long p1
     const int2 pr = pairs[k];
     need[pr.x] = 1; need[pr.y] = 1;
 }
-cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int n, cudaStream_t st) {
+__global__ void need_compact_kernel(const unsigned char* need, int n, int* list, int* count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n && need[t]) list[atomicAdd(count, 1)] = t;
+}
+// need[t] = 1 for both ends of the pairs in [p0, p1); list / count: the same tetrads as a compact list (any order)
+cudaError_t launch_mark_needed(const int2* pairs, long long p0, long long p1, unsigned char* need, int* list, int* count,
+                               int n, cudaStream_t st) {
     cudaError_t err = cudaMemsetAsync(need, 0, (size_t)n, st);
+    if (err != cudaSuccess) return err;
+    err = cudaMemsetAsync(count, 0, sizeof(int), st);
     if (err != cudaSuccess || p1 <= p0) return err;
     mark_needed_kernel<<<(unsigned)((p1 - p0 + 255) / 256), 256, 0, st>>>(pairs, p0, p1, need);
+    need_compact_kernel<<<(n + 255) / 256, 256, 0, st>>>(need, n, list, count);
     return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(128, 10) group_bounds_kernel(const double* crd, const int* param_id, const int* perm,
-                                                            double* gb, int n, int S, const unsigned char* need) {
+                                                            double* gb, int n, int S, const int* need_list, int need_count) {
     const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= n) return;
-    if (!need[t]) return;        // not an end of any pair in this engine's scan slice (sharded runs)
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= need_count) return;
+    const int t = need_list[i];  // an end of some pair in this engine's scan slice (sharded runs: a fraction of all)
     group_bounds_tetrad(crd + (size_t)t * 3 * S, perm + (size_t)param_id[t] * kMaxStride, gb, n, t, S, lane);
 }
 
@@ -563,7 +572,7 @@ __global__ void __launch_bounds__(32 * kBlkWarps, 12) nb_scan_blocks_kernel(Scan
 cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                                 long long p0, long long p1, int n, int S, double cut2_eff, int sms, double* gb,
                                 unsigned long long* work, long long work_items, unsigned* count, int dense_min,
-                                const int* param_id, const int* perm, const unsigned char* need,
+                                const int* param_id, const int* perm, const int* need_list, int need_count,
                                 unsigned long long* const* peers, int world, cudaStream_t st) {
     if (p1 <= p0) return cudaSuccess;
     if (!peers) {
@@ -573,7 +582,8 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
     // work buffer: one CullItem per listed pair at most; the two item counters were zeroed by the caller
     CullItem* items = reinterpret_cast<CullItem*>(work);
     CullItem* items_back = items + (work_items - 1);
-    group_bounds_kernel<<<(n + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need);
+    if (need_count > 0)
+        group_bounds_kernel<<<(need_count + 3) / 4, 128, 0, st>>>(crd, param_id, perm, gb, n, S, need_list, need_count);
     const long long want = p1 - p0;
     pair_select_kernel<<<(unsigned)((want + 127) / 128), 128, 0, st>>>(gb, pairs, p0, p1, sqrt(cut2_eff), items, items_back, count,
                                                                      dense_min, n);
@@ -589,7 +599,9 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
         nb_scan_blocks_kernel<<<(int)((warps + kBlkWarps - 1) / kBlkWarps), 32 * kBlkWarps, 0, st>>>(A, items, count, param_id, perm);
     }
     if (dense_min <= 64) {        // (dense_min > 64: no mask is dense, block kernel only)
-        const int grid = (int)(want < 2 * blocks_wanted ? want : 2 * blocks_wanted);
+        // (its CTAs walk the list with a grid stride; a resident grid suffices and costs little when the list is empty)
+        const long long resident = 30LL * sms;
+        const int grid = (int)(want < resident ? want : resident);
         nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, items_back, count + 1, param_id, perm);
     }
     return cudaGetLastError();
