@@ -820,15 +820,6 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_warp_kernel(EdArgs A) 
     }
 }
 
-// Grid for a kernel whose warps walk `units` work units with a grid stride: every warp gets ceil(units / slots)
-// units or one less, where slots = the warps the machine holds at once — no thin last wave.
-static int balanced_ctas(int units, int warps_per_cta, int sms, int warps_per_sm) {
-    const long long slots = (long long)sms * warps_per_sm;
-    const long long per_warp = (units + slots - 1) / slots;
-    const long long warps = per_warp > 0 ? (units + per_warp - 1) / per_warp : 1;
-    return (int)((warps + warps_per_cta - 1) / warps_per_cta);
-}
-
 cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const double* crd_in, double* sup, int t0, int count,
                              int variant, int sms, cudaStream_t st) {
     if (count <= 0) return cudaSuccess;
@@ -840,7 +831,10 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
     else {
         // (fewer CTAs per SM — tried by padding the CTA with unused shared memory — is monotonically slower:
         // 1.15 / 1.16 / 1.20 / 1.21 / 1.31 ms of ED at 8 / 7 / 6 / 5 / 4 CTAs per SM: the kernel lives on occupancy)
-        const int grid = balanced_ctas((count + 1) / 2, kS2Warps, sms, 8 * kS2Warps);
+        // One tetrad pair per warp.  (A "balanced" grid — every warp the same number of pairs, no thin last wave — was
+        // measured SLOWER at 1e5 and at 12,500 tetrads: short CTAs handed out by the hardware scheduler beat long ones.)
+        const int grid = ((count + 1) / 2 + kS2Warps - 1) / kS2Warps;
+        (void)sms;
         if (ps.S == kMaxStride) superpose2_kernel<kMaxStride><<<grid, 32 * kS2Warps, 0, st>>>(B);
         else                    superpose2_kernel<0><<<grid, 32 * kS2Warps, 0, st>>>(B);
     }

@@ -521,7 +521,7 @@ int do_random(edmd_engine* e, int mode, long time0, int rank, long calls_before,
     // beside other kernels: a resident grid of rng_ctas_per_sm CTAs per SM, so that the generator takes a fixed
     // slice of every SM for most of the step instead of the whole machine for a part of it
     CK(launch_random_terms(e->ps, e->d_noise, e->d_param_id, e->rnd, e->t0, e->t1 - e->t0, e->sp, time0, rank,
-                           calls_before + e->t0, calls_dev, side ? e->sms * e->rng_ctas_per_sm : -e->sms, on));
+                           calls_before + e->t0, calls_dev, side ? e->sms * e->rng_ctas_per_sm : 0, on));
     if (!side) timer_end(e, T_RNG, 1); else e->launches++;
     e->rnd_zero = false;
     return 0;

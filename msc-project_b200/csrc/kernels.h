@@ -94,7 +94,7 @@ cudaError_t build_halo_list(const int2* pairs, long long np, long long p0, long 
 // glibc-rand()/Kinderman-Monahan random terms, one warp per tetrad (rng.cu)
 cudaError_t launch_random_terms(const ParamSets& ps, const double* noise, const int* param_id, double* rnd, int t0, int count,
                                 const SimParams& sp, long time0, int rank, long calls_before,
-                                const long* calls_dev, int max_ctas /* 0: one tetrad per warp; > 0: at most that many CTAs; -sms: balanced */, cudaStream_t st);
+                                const long* calls_dev, int max_ctas /* 0: one tetrad per warp; > 0: at most that many CTAs */, cudaStream_t st);
 cudaError_t launch_ps_precompute(const ParamSets& ps, int P, double* pre, cudaStream_t st);
 cudaError_t launch_noise_table(const ParamSets& ps, int P, double* noise, const SimParams& sp, cudaStream_t st);
 cudaError_t launch_bump_counter(long* counter, long by, cudaStream_t st);
