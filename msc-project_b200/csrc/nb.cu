@@ -599,8 +599,10 @@ cudaError_t launch_nb_scan_cull(const double* crd, const int* natoms, const int2
         nb_scan_blocks_kernel<<<(int)((warps + kBlkWarps - 1) / kBlkWarps), 32 * kBlkWarps, 0, st>>>(A, items, count, param_id, perm);
     }
     if (dense_min <= 64) {        // (dense_min > 64: no mask is dense, block kernel only)
-        // (its CTAs walk the list with a grid stride; a resident grid suffices and costs little when the list is empty)
-        const long long resident = 30LL * sms;
+        // (its CTAs walk the list with a grid stride.  With the steric cutoff alone (sqrt(2) A) a pair rarely has nine
+        // candidate blocks, and an almost idle grid of 4,440 one-warp CTAs would cost 16 us per step: a small grid then,
+        // two residents' worth when the cutoff is the electrostatic one)
+        const long long resident = (cut2_eff > 4.0 ? 30LL : 4LL) * sms;
         const int grid = (int)(want < resident ? want : resident);
         nb_scan_cull_kernel<<<grid, kScanThreads, 0, st>>>(A, items_back, count + 1, param_id, perm);
     }
