@@ -4,26 +4,26 @@
 // accumulation of Worker::force_Calculation (src/worker.cpp:165-179, 191-199) and the clip of
 // Master::process_NB_Forces (src/master.cpp:297-322).
 //
-// Two kernels:
+// Two stages:
 //
-//  nb_scan_kernel — the FP64 hot loop.  For every listed tetrad pair it evaluates the squared
-//    distance of all num_Atoms x num_Atoms atom pairs (the 9 algorithmic flops per atom pair
-//    of edmd.cpp:251-256) and records whether ANY atom pair can contribute
-//    (r^2 below the effective cutoff).  A CTA of 64 threads owns one tetrad pair at a time; each
-//    thread holds 4 atoms of one tetrad in registers; the other tetrad's SoA planes sit in
-//    shared memory (the next partner's 6 KB block is fetched by ONE TMA bulk copy —
-//    cp.async.bulk + mbarrier — while the current pair is computed) and are read as 128-bit
-//    broadcasts (two atoms per LDS), software-pipelined one step ahead.  The cutoff test is an
-//    integer min over the high words of r^2 (r^2 >= 0, so the IEEE bit pattern is monotonic) on
-//    the ALU pipe, leaving the FP64 pipe only the distance arithmetic.  Output: one byte per
-//    pair.  Roofline: FP64 pipe.
+//  distance pass — decides which 32 x 32 atom blocks of which listed tetrad pairs can hold an atom pair
+//    that contributes (r^2 below the effective cutoff) and leaves one 64-bit block mask per pair (0 = the
+//    pair is not flagged).  Default (edmd_set_nb_scan_mode(4)): exact bounding-sphere culling — group and
+//    tetrad spheres (group_bounds_kernel, bounds.cuh), sphere tests per listed pair (pair_select_kernel), then
+//    the candidate blocks are evaluated with the biased Gram arithmetic by nb_scan_blocks_kernel (sparse
+//    masks: one atom per lane, 48 warps per SM) or nb_scan_cull_kernel (dense masks: 8-atom register tile,
+//    partner by one TMA bulk copy).  Brute force (modes 0-2, nb_scan_kernel / nb_scan32_kernel): all
+//    num_Atoms x num_Atoms atom pairs of every listed pair, the 9 algorithmic flops per atom pair of
+//    edmd.cpp:251-256 in 3 DFMA; this is the kernel the FP64 roofline is defined on.  The
+//    cutoff test is an integer min over the high words (r^2 >= 0, so the IEEE bit pattern is monotonic) on
+//    the ALU pipe, leaving the FP64 pipe only the distance arithmetic.
 //
-//  nb_accumulate_kernel — one CTA per tetrad walks that tetrad's partners in pair-list order
-//    and, for flagged pairs only, re-evaluates the pair with the reference's exact expression
-//    tree (no FMA contraction, IEEE division) and the reference's summation order: inner sum
-//    over the partner's atoms ascending starting from 0, then added to the tetrad total in
-//    pair-list order.  Each tetrad's forces are produced by exactly one CTA in a fixed order —
-//    no atomics, bit-stable, and (forces) bit-identical to the W = 1 reference.  Then the clip.
+//  force pass — nb_force_kernel: one warp per (marked tetrad, slot group) re-evaluates the masked blocks
+//    of the tetrad's flagged pairs with the reference's exact expression tree (no FMA contraction, IEEE
+//    division) and the reference's summation order: per atom over the partner's atoms ascending starting
+//    from +0.0, then added to the tetrad total in pair-list order.  Each atom's force is produced by exactly
+//    one lane in a fixed order — no atomics, bit-stable, and bit-identical to the W = 1 reference.  Then
+//    the clip, and the velocity / coordinate update (finish_*_kernel).
 //
 // With qfac = 0 (the reference's hard-coded value) an atom pair changes the result only if
 // r^2 < 2 (a = max(0, 2 - r^2) > 0): in-cutoff pairs with a = 0 add +-0.0.  The effective cutoff
@@ -84,7 +84,7 @@ constexpr int kScanCtasPerSm = 12;
 //   the pair unconditionally), so the high-word integer test applies: hi(c) <= hi(thr_i) + 1.
 //   Rounding error of the chain <= 2^-51 (|xi'|+|xj'|)^2 + 2^-51 B ~ 1e-11, slack of the test
 //   >= 2^-20 thr_i >= 2e-6: a superset of the true hits, always.
-//   Either way the scan only SELECTS pairs: the forces come from nb_accumulate_kernel's exact
+//   Either way the scan only SELECTS pairs: the forces come from nb_force_kernel's exact
 //   arithmetic, so both modes give bit-identical results.
 //
 // Instruction-issue budget (measured on B200: an FP64 warp instruction holds the dispatch port

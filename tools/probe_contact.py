@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("msc-project_b200")
 
-def run(n, kind, laps, qfac, steps=20, random_mode=0, lap_gap=9.0):
+def run(n, kind, laps, qfac, steps=20, random_mode=0, lap_gap=40.0):
     s = pkg.make_ring(n, kind=kind, laps=laps, lap_gap=lap_gap)
     g = pkg.Engine(s)
     g.set_nb_consts(100.0, qfac)
@@ -30,7 +30,7 @@ def run(n, kind, laps, qfac, steps=20, random_mode=0, lap_gap=9.0):
 
 if __name__ == "__main__":
     args = [int(x) for x in sys.argv[1:]]
-    cases = list(zip(args[0::2], args[1::2])) or [(10000, 50), (10000, 10), (100000, 500), (100000, 100)]
+    cases = list(zip(args[0::2], args[1::2])) or [(10000, 2), (100000, 2)]   # (many laps in one annulus = millions of pairs)
     for n, laps in cases:
         run(n, "ring", 1, 0.0)
         for qfac in (0.0, 332.064 / 4.0):
