@@ -1,4 +1,4 @@
-"""[torchrun] tools/dist_perf.py N_TETRADS [steps random_mode kind laps lap_gap qfac] : step time of the (sharded) engine.
+"""[torchrun] tools/dist_perf.py N_TETRADS [steps random_mode kind laps lap_gap qfac scan_mode] : step time of the (sharded) engine.
 The timed steps run as the engine runs them in production (one CUDA graph per step, in-engine barriers);
 a second short pass with the per-phase timers on gives the breakdown."""
 import importlib, json, os, sys, time
@@ -16,9 +16,11 @@ a = sys.argv[1:]
 n = int(a[0]); steps = int(a[1]) if len(a) > 1 else 20; random_mode = int(a[2]) if len(a) > 2 else 1
 kind = a[3] if len(a) > 3 else "ring"; laps = int(a[4]) if len(a) > 4 else 2; gap = float(a[5]) if len(a) > 5 else 40.0
 qfac = float(a[6]) if len(a) > 6 else 0.0
+scan_mode = int(a[7]) if len(a) > 7 else 4
 s = pkg.make_ring(n, kind=kind, laps=laps, lap_gap=gap)
 g = pkg.Engine(s, device=local)
 g.set_nb_consts(100.0, qfac)
+g.set_nb_scan_mode(scan_mode)
 sh = dmod.ShardedEngine(dmod.EngineBackend(g, torch.device("cuda", local)), dist, s.n, rank, world)
 sh.set_rng(1000000000, 1, 0); g.set_rng(1000000000, 1, 0)
 if world == 1:
@@ -37,7 +39,7 @@ ph = {nm: round(g.timing_get(i)[0] / 5, 4) for nm, i in (("ed", 0), ("rng", 3), 
 g.timing(False)
 t0 = time.time(); sh.merge(); npairs2 = sh.build_pairlist(); g.sync(); t_rebuild = time.time() - t0
 if rank == 0:
-    print(json.dumps(dict(n=n, world=world, kind=kind, laps=laps, gap=gap, qfac=qfac, random=random_mode, pairs=npairs,
+    print(json.dumps(dict(n=n, world=world, kind=kind, laps=laps, gap=gap, qfac=qfac, random=random_mode, scan_mode=scan_mode, pairs=npairs,
                           first_build_s=round(tb, 3), merge_rebuild_ms=round(t_rebuild * 1e3, 2), ms_per_step=round(float(t), 4),
                           host_enqueue_ms=round(t_host / steps * 1e3, 4), phases_rank0=ph, **st)), flush=True)
 sh.close()
