@@ -450,7 +450,8 @@ int do_scan(edmd_engine* e) {
                                e->d_gb, e->d_pmask, e->pmask_cap, reinterpret_cast<unsigned*>(e->d_mark + e->n + 2), e->cull_dense_min,
                                e->d_param_id, e->d_perm, e->d_need_list, e->need_count,
                                e->peer_mode ? e->d_hit_tbl : nullptr, e->world, e->st));
-        timer_end(e, T_SCAN, e->p1 > e->p0 ? 3 : 0);
+        // kernels of the pass: bounding spheres, pair selection, block kernel (sparse masks), tiled kernel (dense masks)
+        timer_end(e, T_SCAN, e->p1 > e->p0 ? (e->need_count > 0) + 1 + (e->cull_dense_min > 1) + (e->cull_dense_min <= 64) : 0);
         e->hits_valid = true;
         return 0;
     }
