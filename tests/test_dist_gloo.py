@@ -202,3 +202,81 @@ def test_halo_plan_lists(edmd):
         want = sorted(t for t in used if not (pl.t0 <= t < pl.t1))
         assert hp.recv_idx.tolist() == want
         assert hp.recv_counts.sum() == len(want)
+
+
+class _FakeDist:
+    """Single-process stand-in for torch.distributed (world 2 seen from rank 0): records the collectives."""
+
+    def __init__(self, log, world):
+        self.log, self.world = log, world
+
+    def all_gather_object(self, out, obj, group=None):
+        self.log.append("all_gather_object")
+        for i in range(len(out)):
+            out[i] = obj
+
+    def barrier(self, group=None):
+        self.log.append("barrier")
+
+
+class _FakeNativeBackend:
+    """Records what ShardedEngine asks of a backend that runs the sharded step itself (the GPU engine's peer API)."""
+
+    def __init__(self, log, npairs_seq, outgrow_at=None):
+        self.log, self.npairs_seq, self.builds, self.outgrow_at = log, list(npairs_seq), 0, outgrow_at
+        self.attached = False
+
+    def peer_export(self):
+        self.log.append("export"); return b"x" * 320
+
+    def peer_attach(self, blobs, world, rank):
+        assert len(blobs) == 320 * world
+        self.log.append("attach"); self.attached = True
+
+    def peer_detach(self):
+        self.log.append("detach"); self.attached = False
+
+    def peer_gather(self, what):
+        self.log.append(f"gather{what}")
+
+    def build_pairlist(self):
+        self.builds += 1
+        if self.outgrow_at == self.builds and self.attached:
+            self.log.append("build!outgrew")
+            raise RuntimeError("edmd_b200 error -3: pair list of 99 pairs outgrew the peer-visible mask buffer (64)")
+        self.log.append("build")
+        return self.npairs_seq[min(self.builds, len(self.npairs_seq)) - 1]
+
+    def set_shard(self, t0, t1, p0, p1): self.log.append(("shard", t0, t1, p0, p1))
+    def engine_step(self, nsteps, mode): self.log.append(("step", nsteps, mode))
+    def engine_set_rng(self, time0, rank, calls): self.log.append("set_rng")
+    def merge(self): self.log.append("merge")
+    def sync(self): self.log.append("sync")
+
+
+def test_native_protocol_sequence():
+    """The one-process-per-GPU glue around the in-engine multi-GPU step (dist.py, native path): handles are
+    exchanged once, the shard follows the pair count, a rebuild right after a merge does not gather twice, and a
+    pair list that outgrew the mapped mask buffer is answered by detach -> rebuild -> export -> attach."""
+    dmod = importlib.import_module("msc-project_b200.dist")
+    log = []
+    b = _FakeNativeBackend(log, [101, 103, 99], outgrow_at=3)
+    sh = dmod.ShardedEngine(b, _FakeDist(log, 2), 40, 0, 2, native=True)
+    assert sh.native and not sh.replicate
+    assert sh.build_pairlist() == 101
+    assert log == ["build", "export", "all_gather_object", "attach", "barrier", ("shard", 0, 20, 0, 51)]
+    del log[:]
+    sh.step(5, 1)
+    assert log == [("step", 5, 1)] and sh.calls == 5 * 40
+    del log[:]
+    sh.merge()
+    assert sh.build_pairlist() == 103                     # coordinates are complete after the merge: no second gather
+    assert log == ["gather3", "merge", "build", ("shard", 0, 20, 0, 52)]
+    del log[:]
+    sh.step(1, 0)
+    assert sh.build_pairlist() == 99                      # stepped since: gather first; then the outgrow path
+    assert log == [("step", 1, 0), "gather1", "build!outgrew", "barrier", "detach", "barrier", "build", "export",
+                   "all_gather_object", "attach", "barrier", ("shard", 0, 20, 0, 50)]
+    del log[:]
+    sh.finish(); sh.close()
+    assert log == ["gather7", "sync", "barrier", "detach", "barrier"]
