@@ -92,7 +92,9 @@ int  edmd_set_nb_scan_mode(edmd_engine* e, int mode);
 /* Projection kernel of the ED pass (edmd.cpp:106-150): 0 = automatic (default), 1 = one CTA per tetrad
  * with the eigenvector coefficients in registers (any number of eigenvectors), 2 = one warp per
  * tetrad with the parameter set staged in shared memory (sets with <= 12 eigenvectors; chosen
- * automatically when tetrads share parameter sets).  Same arithmetic up to the order of one tree sum. */
+ * automatically when tetrads share parameter sets), 3 = the two passes as FP64 tensor-core contractions
+ * (DMMA.8x8x4) over groups of eight tetrads that share a set (sets with <= 12 eigenvectors; falls back to 1
+ * otherwise).  Same arithmetic up to the order of the projection sums. */
 int  edmd_set_ed_kernel(edmd_engine* e, int which);
 
 /* ---- data in / out ----------------------------------------------------------------- */

@@ -1,0 +1,324 @@
+// ed_mma.cu — the ED projection (edmd.cpp:89-157) as two small contractions on the FP64 tensor cores.
+//
+// For tetrads that share a parameter set the two passes of EDMD::calculate_ED_Forces over the eigenvector
+// block E [12][3 N_a] are matrix products:
+//
+//   pass 1   P [12 x T]     =  E  . D          D [3 N_a x T]: displacements d = R x_c - avg_c of T tetrads   (edmd.cpp:106-110)
+//   pass 2   S'[3 N_a x T]  =  E^T . P  + avg                 re-embedded coordinates                          (edmd.cpp:113-127)
+//            F'[3 N_a x T]  =  E^T . (-P scaled / eval)       force in the reference frame
+//
+// ed_project_warp_kernel (ed.cu) evaluates them one tetrad per warp with scalar DFMAs and reads every
+// coefficient of E from shared memory once per pass and tetrad: 147 KB = 1,390 shared-memory wavefronts per
+// tetrad, which is what bounds it (profiles/ncu_r02_c3_step_details.txt).  Here T = 8 tetrads form the N
+// dimension of mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), so a coefficient fetched from shared memory is used for eight
+// tetrads: 84 + 72 shared-memory loads per lane and tetrad group instead of 8 x 576.
+//
+// One CTA (8 warps) walks a run of tetrads that share a parameter set, eight at a time:
+//   pass 1   warp w owns atoms 32w..32w+31 (the K range of the contraction): lane (g = lane/4, r = lane%4) loads
+//            atom 32w + 4s + r of tetrad g, s = 0..7, forms its displacement with the reference's expressions and
+//            feeds it as the B fragment of six DMMAs per s (3 planes x rows 0-7 / 8-11 of E); the A fragments come
+//            from the staged E, whose row stride 3S + 4 doubles makes both passes' fragment loads conflict-free.
+//            The warp's partial P goes to shared memory; after ONE CTA barrier every warp adds the eight partials
+//            in warp order (fixed order: bit-stable, independent of how tetrads are grouped).
+//   pass 2   warp w owns the same 32 atoms as four 8-atom M tiles; K = the 12 eigenvectors in three steps; the
+//            accumulators start from avg (S') and 0 (F'); the D fragment leaves lane (g, r) with atom 8 tau + g of
+//            tetrads 2r and 2r + 1, all three components, which it rotates back to the laboratory frame
+//            (edmd.cpp:130-150) and stores.
+// Every column of an MMA is computed independently of the others, so a tetrad's result does not depend on which
+// other tetrads share its group: the results are identical for every shard layout / number of GPUs.
+// Same arithmetic as the other projection kernels up to the order of the twelve projection sums (~1e-16).
+// Compiled with -fmad=false like ed.cu (the displacement and the back-rotation round like the CPU build).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace edmd {
+namespace {
+
+constexpr int kGroup = 8;                       // tetrads per group: the N dimension of the MMA tile
+constexpr int kRows = kNevReg;                  // eigenvector rows staged (12)
+constexpr int kPartRow = kRows * kGroup;        // doubles per warp of partial projections
+constexpr int kSupW = kSupWordsHost;            // doubles per tetrad of superposition scratch (ed.cu)
+
+// D (8x8) += A (8x4, row) . B (4x8, col).  Fragments (PTX ISA, mma.m8n8k4 .f64), g = lane >> 2, r = lane & 3:
+//   A: one double, row g, column r;  B: one double, row r, column g;  C/D: two doubles, row g, columns 2r and 2r + 1.
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+struct MmaArgs {
+    ParamSets ps;
+    const int* param_id;
+    const double* crd_in;  // [n][3][S] current coordinates
+    double* crd;           // [n][3][S] out: the re-embedded coordinates (may alias crd_in)
+    double* fed;           // [n][3][S] out
+    double* e_ed;          // [n] out
+    const double* sup;     // [n][kSupW] from the superposition kernel: R, shift, centroid of avg, centroid of x
+    double scaled;
+    const int* order;      // [count] tetrads of this launch sorted by parameter set
+    int count;
+    int chunk;             // tetrads per CTA (a multiple of kGroup)
+};
+
+template <int SC>   // SC: the atom stride when it is the usual 256 (shared-memory offsets fold into immediates), else 0
+__global__ void __launch_bounds__(kThreads, 2) ed_project_mma_kernel(MmaArgs A) {
+    extern __shared__ double msm[];
+    const unsigned full = 0xffffffffu;
+    const int S = SC ? SC : A.ps.S;
+    const int SP = 3 * S + 4;                   // 2 SP = 8 (mod 32) words: rows 8 banks apart
+    double* sEV = msm;                          // [kRows][SP]
+    double* sAV = sEV + kRows * SP;             // [3][S]
+    double* sPart = sAV + 3 * S;                // [2][kWarps][kRows][kGroup]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __reduce_max_sync(full, tid >> 5);
+    const int g = lane >> 2, r = lane & 3;
+    const int e0 = blockIdx.x * A.chunk;
+    const int e1 = (e0 + A.chunk < A.count) ? e0 + A.chunk : A.count;
+    const int nblk = S >> 5;                    // 32-atom blocks of a tetrad = warps with work
+    const bool active = warp < nblk;
+    const int ab = 32 * warp;                   // first atom of this warp's block
+
+    int buf = 0;
+    int base = e0;
+    while (base < e1) {
+        const int ps = __reduce_max_sync(full, A.param_id[A.order[base]]);
+        const int na = __reduce_max_sync(full, A.ps.na[ps]), nev = __reduce_max_sync(full, A.ps.nev[ps]);
+        {   // stage the set's tables (rows >= NEV are zero; the arrays are zero-padded beyond na / nev)
+            const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
+            const double* AV = A.ps.avg + (size_t)ps * 3 * S;
+            const int rows = A.ps.NEV < kRows ? A.ps.NEV : kRows;
+            for (int i = tid; i < kRows * 3 * S; i += kThreads) {
+                const int j = i / (3 * S), c = i - j * (3 * S);
+                sEV[j * SP + c] = j < rows ? EV[i] : 0.0;
+            }
+            for (int i = tid; i < 3 * S; i += kThreads) sAV[i] = AV[i];
+        }
+        __syncthreads();
+        double el[3];                           // eigenvalues of the rows this lane holds as B fragments in pass 2
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int j = r + 4 * q;
+            el[q] = j < nev ? A.ps.eval[(size_t)ps * A.ps.NEV + j] : 1.0;
+        }
+
+        int ge = base;
+        for (;;) {
+            // the group: up to eight consecutive entries of `order` that share the set (every warp derives it alike)
+            int my_t = 0;
+            bool ok = false;
+            if (lane < kGroup && ge + lane < e1) { my_t = A.order[ge + lane]; ok = A.param_id[my_t] == ps; }
+            const unsigned m = __ballot_sync(full, ok) & 0xffu;
+            const int ng = __ffs(~m) - 1;       // leading run of valid entries, 0..8
+            if (ng == 0) break;
+            if (ng == kGroup) {                 // start the next group's coordinates on their way into L2
+                const int per = 3 * S / 16;     // 128-byte lines per tetrad
+                for (int line = tid; line < kGroup * per; line += kThreads) {
+                    const int u = line / per, o = line - u * per;
+                    const int en = ge + kGroup + u;
+                    if (en < e1) prefetch_l2(A.crd_in + (size_t)A.order[en] * 3 * S + o * 16);
+                }
+            }
+
+            // ---- pass 1: partial projections over this warp's 32 atoms
+            const int tg = __shfl_sync(full, my_t, g);
+            if (active) {
+                const bool colv = g < ng;
+                double R[9], ca[3], cx[3];
+#pragma unroll
+                for (int q = 0; q < 9; q++) R[q] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) ca[q] = cx[q] = 0.0;
+                const double* XIN = A.crd_in;
+                if (colv) {
+                    const double* SUP = A.sup + (size_t)tg * kSupW;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) R[q] = SUP[q];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) { ca[q] = SUP[12 + q]; cx[q] = SUP[15 + q]; }
+                    XIN = A.crd_in + (size_t)tg * 3 * S;
+                }
+                double x[8][3];
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    const int a = ab + 4 * s + r;
+                    x[s][0] = x[s][1] = x[s][2] = 0.0;
+                    if (colv && a < na) { x[s][0] = XIN[a]; x[s][1] = XIN[S + a]; x[s][2] = XIN[2 * S + a]; }
+                }
+                double acc[2][3][2];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[mt][c][0] = acc[mt][c][1] = 0.0;
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    const int a = ab + 4 * s + r;
+                    double d[3] = {0.0, 0.0, 0.0};
+                    if (colv && a < na) {       // edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
+                        const double ac0 = sAV[a] - ca[0], ac1 = sAV[S + a] - ca[1], ac2 = sAV[2 * S + a] - ca[2];
+                        const double xc0 = x[s][0] - cx[0], xc1 = x[s][1] - cx[1], xc2 = x[s][2] - cx[2];
+                        d[0] = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
+                        d[1] = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
+                        d[2] = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {   // edmd.cpp:106-110: rows 0-7 and rows 8-11 (+ four zero rows) of E
+                        const double a_lo = sEV[g * SP + c * S + a];
+                        const double a_hi = g < 4 ? sEV[(8 + g) * SP + c * S + a] : 0.0;
+                        dmma(acc[0][c], a_lo, d[c]);
+                        dmma(acc[1][c], a_hi, d[c]);
+                    }
+                }
+                double* part = sPart + (size_t)(buf * kWarps + warp) * kPartRow;
+                {
+                    const double p0 = (acc[0][0][0] + acc[0][1][0]) + acc[0][2][0];
+                    const double p1 = (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1];
+                    *reinterpret_cast<double2*>(part + g * kGroup + 2 * r) = make_double2(p0, p1);
+                }
+                if (g < 4) {
+                    const double p0 = (acc[1][0][0] + acc[1][1][0]) + acc[1][2][0];
+                    const double p1 = (acc[1][0][1] + acc[1][1][1]) + acc[1][2][1];
+                    *reinterpret_cast<double2*>(part + (8 + g) * kGroup + 2 * r) = make_double2(p0, p1);
+                }
+            }
+            __syncthreads();
+
+            if (active) {
+                // ---- the projections of tetrad g on eigenvectors r, r + 4, r + 8: the B fragments of pass 2
+                double P[3], W[3], term[3];
+                {
+                    const double* pb = sPart + (size_t)buf * kWarps * kPartRow;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int o = (r + 4 * q) * kGroup + g;
+                        double s = pb[o];
+                        for (int w = 1; w < nblk; w++) s += pb[w * kPartRow + o];
+                        P[q] = s;
+                        W[q] = -(s * A.scaled / el[q]);
+                        term[q] = s * s / el[q];
+                    }
+                }
+                if (warp == 0) {                // edmd.cpp:153-157, summed in eigenvector order
+                    double en = 0.0;
+#pragma unroll
+                    for (int j = 0; j < kRows; j++) {
+                        const double v = __shfl_sync(full, term[j >> 2], (lane & ~3) | (j & 3));
+                        if (j < nev) en += v;
+                    }
+                    if (r == 0 && g < ng) A.e_ed[tg] = en * (0.5 * A.scaled);
+                }
+
+                // ---- pass 2: re-embedding and force (edmd.cpp:113-127), back to the laboratory frame (:130-150)
+                const int ta = __shfl_sync(full, my_t, 2 * r), tb = __shfl_sync(full, my_t, 2 * r + 1);
+                const bool va = 2 * r < ng, vb = 2 * r + 1 < ng;
+                double Ra[9], sha[3], Rb[9], shb[3];
+#pragma unroll
+                for (int q = 0; q < 9; q++) Ra[q] = Rb[q] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) sha[q] = shb[q] = 0.0;
+                if (va) {
+                    const double* SUP = A.sup + (size_t)ta * kSupW;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) Ra[q] = SUP[q];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) sha[q] = SUP[9 + q];
+                }
+                if (vb) {
+                    const double* SUP = A.sup + (size_t)tb * kSupW;
+#pragma unroll
+                    for (int q = 0; q < 9; q++) Rb[q] = SUP[q];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) shb[q] = SUP[9 + q];
+                }
+#pragma unroll
+                for (int tau = 0; tau < 4; tau++) {
+                    const int a = ab + 8 * tau + g;
+                    double sv[3][2], fv[3][2];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        sv[c][0] = sv[c][1] = sAV[c * S + a];
+                        fv[c][0] = fv[c][1] = 0.0;
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            const double ev = sEV[(4 * q + r) * SP + c * S + a];
+                            dmma(sv[c], ev, P[q]);
+                            dmma(fv[c], ev, W[q]);
+                        }
+                    }
+                    if (a < na) {
+                        if (va) {
+                            const double s0 = sv[0][0] - sha[0], s1 = sv[1][0] - sha[1], s2 = sv[2][0] - sha[2];
+                            const double f0 = fv[0][0], f1 = fv[1][0], f2 = fv[2][0];
+                            double* X = A.crd + (size_t)ta * 3 * S;
+                            double* F = A.fed + (size_t)ta * 3 * S;
+                            X[a]         = Ra[0] * s0 + Ra[3] * s1 + Ra[6] * s2;
+                            X[S + a]     = Ra[1] * s0 + Ra[4] * s1 + Ra[7] * s2;
+                            X[2 * S + a] = Ra[2] * s0 + Ra[5] * s1 + Ra[8] * s2;
+                            F[a]         = Ra[0] * f0 + Ra[3] * f1 + Ra[6] * f2;
+                            F[S + a]     = Ra[1] * f0 + Ra[4] * f1 + Ra[7] * f2;
+                            F[2 * S + a] = Ra[2] * f0 + Ra[5] * f1 + Ra[8] * f2;
+                        }
+                        if (vb) {
+                            const double s0 = sv[0][1] - shb[0], s1 = sv[1][1] - shb[1], s2 = sv[2][1] - shb[2];
+                            const double f0 = fv[0][1], f1 = fv[1][1], f2 = fv[2][1];
+                            double* X = A.crd + (size_t)tb * 3 * S;
+                            double* F = A.fed + (size_t)tb * 3 * S;
+                            X[a]         = Rb[0] * s0 + Rb[3] * s1 + Rb[6] * s2;
+                            X[S + a]     = Rb[1] * s0 + Rb[4] * s1 + Rb[7] * s2;
+                            X[2 * S + a] = Rb[2] * s0 + Rb[5] * s1 + Rb[8] * s2;
+                            F[a]         = Rb[0] * f0 + Rb[3] * f1 + Rb[6] * f2;
+                            F[S + a]     = Rb[1] * f0 + Rb[4] * f1 + Rb[7] * f2;
+                            F[2 * S + a] = Rb[2] * f0 + Rb[5] * f1 + Rb[8] * f2;
+                        }
+                    }
+                }
+            }
+            ge += ng;
+            buf ^= 1;                           // the partials are double-buffered: one barrier per group suffices
+            if (ng < kGroup) break;             // the run (or the CTA's chunk) ends inside this group
+        }
+        base = ge;
+        if (base < e1) __syncthreads();         // every warp is done with this set's tables before the next set's arrive
+    }
+}
+
+size_t mma_smem_bytes(int S) { return sizeof(double) * ((size_t)kRows * (3 * S + 4) + 3 * S + 2 * kWarps * kPartRow); }
+
+}  // namespace
+
+bool ed_project_mma_supported(const ParamSets& ps) { return ps.NEV <= kRows && ps.S % 32 == 0 && ps.S <= kMaxStride; }
+
+cudaError_t launch_ed_project_mma(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
+                                  double* e_ed, const double* sup, const int* order, int sms, int count, double scaled,
+                                  cudaStream_t st) {
+    if (count <= 0) return cudaSuccess;
+    if (!ed_project_mma_supported(ps)) return cudaErrorInvalidValue;
+    cudaError_t err;
+    static bool done[64] = {};                  // the opt-in to > 48 KB of dynamic shared memory is per device
+    int dev = 0;
+    err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    bool& configured = done[dev & 63];
+    if (!configured) {
+        const int most = (int)mma_smem_bytes(kMaxStride);
+        err = cudaFuncSetAttribute(ed_project_mma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        if (err != cudaSuccess) return err;
+        err = cudaFuncSetAttribute(ed_project_mma_kernel<kMaxStride>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+        if (err != cudaSuccess) return err;
+        configured = true;
+    }
+    int chunk = (count + 2 * sms - 1) / (2 * sms);          // two resident CTAs per SM, one wave
+    chunk = (chunk + kGroup - 1) / kGroup * kGroup;          // whole groups
+    if (chunk < kGroup) chunk = kGroup;
+    MmaArgs A{ps, param_id, crd_in, crd, fed, e_ed, sup, scaled, order, count, chunk};
+    const size_t smem = mma_smem_bytes(ps.S);
+    const int grid = (count + chunk - 1) / chunk;
+    if (ps.S == kMaxStride) ed_project_mma_kernel<kMaxStride><<<grid, kThreads, smem, st>>>(A);
+    else                    ed_project_mma_kernel<0><<<grid, kThreads, smem, st>>>(A);
+    return cudaGetLastError();
+}
+
+}  // namespace edmd

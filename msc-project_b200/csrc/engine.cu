@@ -153,7 +153,8 @@ struct edmd_engine {
     int rank = 1;
     long calls = 0;
 
-    int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad (edmd_set_ed_kernel)
+    int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad, 3 tensor-core (edmd_set_ed_kernel)
+    bool ed_auto_mma = false;   // what "automatic" picks for shared parameter sets with <= 12 eigenvectors (EDMD_ED_MMA)
     int cull_dense_min = 9;   // sphere masks with this many blocks or more go to the tiled distance kernel (EDMD_CULL_DENSE)
     int sup_variant = 0; // superposition kernel: 0 by size, 1 one tetrad per warp, 2 two tetrads per warp (EDMD_SUPERPOSE)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)
@@ -414,12 +415,21 @@ int do_ed(edmd_engine* e) {
     e->latest_in_crd2 = false;
     // The warp-per-tetrad projection stages a parameter set in shared memory once per run of tetrads that
     // share it: worth it when sets are shared (replicated DNA), not when every tetrad has its own.
-    const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && (long long)e->n >= 8LL * e->P);
+    // The choice depends on the whole system (n, P, NEV), never on the shard: every rank of a multi-GPU run uses the
+    // same kernel, so the results stay identical for every world size.
+    const bool shared_sets = (long long)e->n >= 8LL * e->P;
+    const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && shared_sets);
+    // The tensor-core projection (ed_mma.cu) groups eight tetrads of one parameter set per MMA tile.
+    const bool mma = ed_project_mma_supported(e->ps) && (e->ed_kernel == 3 || (e->ed_kernel == 0 && shared_sets && e->ed_auto_mma));
     timer_begin(e, T_SUP);
     CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->sms, e->st));
     timer_end(e, T_SUP, 0);
-    CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
-                         e->t1 - e->t0, e->sp.scaled, warp, e->st));
+    if (mma)
+        CK(launch_ed_project_mma(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms,
+                                 e->t1 - e->t0, e->sp.scaled, e->st));
+    else
+        CK(launch_ed_project(e->ps, e->d_param_id, src, e->crd, e->fed, e->e_ed, e->sup, e->d_order, e->sms, e->t0,
+                             e->t1 - e->t0, e->sp.scaled, warp, e->st));
     timer_end(e, T_ED, 2);
     return 0;
 }
@@ -599,6 +609,7 @@ int edmd_create(const edmd_params* p, int device, edmd_engine** out) {
     if (const char* v = getenv("EDMD_SUPERPOSE")) { const int k = atoi(v); if (k >= 0 && k <= 2) e->sup_variant = k; }
     if (const char* v = getenv("EDMD_RNG_CTAS")) { const int k = atoi(v); if (k >= 1 && k <= 16) e->rng_ctas_per_sm = k; }
     if (const char* v = getenv("EDMD_RNG_BRANCH")) e->rng_branch = atoi(v) != 0;
+    if (const char* v = getenv("EDMD_ED_MMA")) e->ed_auto_mma = atoi(v) != 0;
     if (const char* v = getenv("EDMD_CULL_DENSE")) { const int k = atoi(v); if (k >= 0 && k <= 65) e->cull_dense_min = k; }
     *out = e;
     return 0;
@@ -647,7 +658,7 @@ int edmd_set_nb_clip(edmd_engine* e, int on) {
 
 int edmd_set_ed_kernel(edmd_engine* e, int which) {
     if (!e) return fail(EDMD_ERR_ARG, "null engine");
-    if (which < 0 || which > 2) return fail(EDMD_ERR_ARG, "ED kernel %d unknown (0 automatic, 1 thread per atom, 2 warp per tetrad)", which);
+    if (which < 0 || which > 3) return fail(EDMD_ERR_ARG, "ED kernel %d unknown (0 automatic, 1 thread per atom, 2 warp per tetrad, 3 tensor core)", which);
     e->ed_kernel = which;
     drop_graph(e);
     return 0;

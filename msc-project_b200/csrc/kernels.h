@@ -20,6 +20,11 @@ cudaError_t launch_superpose(const ParamSets& ps, const int* param_id, const dou
 cudaError_t launch_ed_project(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
                               double* e_ed, double* sup, const int* order, int sms, int t0, int count, double scaled,
                               bool use_warp_kernel, cudaStream_t st);
+// the projection as DMMA contractions over groups of eight tetrads that share a parameter set (ed_mma.cu)
+bool ed_project_mma_supported(const ParamSets& ps);
+cudaError_t launch_ed_project_mma(const ParamSets& ps, const int* param_id, const double* crd_in, double* crd, double* fed,
+                                  double* e_ed, const double* sup, const int* order, int sms, int count, double scaled,
+                                  cudaStream_t st);
 
 cudaError_t launch_nb_scan(const double* crd, const int* natoms, const int2* pairs, unsigned long long* hit,
                            long long p0, long long p1, int S, double cut2_eff, int mode, int sms,
