@@ -64,26 +64,25 @@ struct MmaArgs {
 template <int SC>   // SC: the atom stride when it is the usual 256 (shared-memory offsets fold into immediates), else 0
 __global__ void __launch_bounds__(kThreads, 2) ed_project_mma_kernel(MmaArgs A) {
     extern __shared__ double msm[];
+    __shared__ int sNext, sGrab;
     const unsigned full = 0xffffffffu;
     const int S = SC ? SC : A.ps.S;
     const int SP = 3 * S + 4;                   // 2 SP = 8 (mod 32) words: rows 8 banks apart
     double* sEV = msm;                          // [kRows][SP]
     double* sAV = sEV + kRows * SP;             // [3][S]
-    double* sPart = sAV + 3 * S;                // [2][kWarps][kRows][kGroup]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __reduce_max_sync(full, tid >> 5);
+    double* sXp = sAV + 3 * S + warp * kPartRow;   // this warp's [kRows][kGroup] scratch: projections, D -> B fragment layout
     const int g = lane >> 2, r = lane & 3;
     const int e0 = blockIdx.x * A.chunk;
     const int e1 = (e0 + A.chunk < A.count) ? e0 + A.chunk : A.count;
-    const int nblk = S >> 5;                    // 32-atom blocks of a tetrad = warps with work
-    const bool active = warp < nblk;
-    const int ab = 32 * warp;                   // first atom of this warp's block
+    const int nblk = S >> 5;                    // 32-atom blocks of a tetrad
 
-    int buf = 0;
     int base = e0;
     while (base < e1) {
         const int ps = __reduce_max_sync(full, A.param_id[A.order[base]]);
         const int na = __reduce_max_sync(full, A.ps.na[ps]), nev = __reduce_max_sync(full, A.ps.nev[ps]);
+        if (tid == 0) { sNext = e1; sGrab = 0; }
         {   // stage the set's tables (rows >= NEV are zero; the arrays are zero-padded beyond na / nev)
             const double* EV = A.ps.evec + (size_t)ps * A.ps.NEV * 3 * S;
             const double* AV = A.ps.avg + (size_t)ps * 3 * S;
@@ -102,110 +101,113 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_mma_kernel(MmaArgs A) 
             el[q] = j < nev ? A.ps.eval[(size_t)ps * A.ps.NEV + j] : 1.0;
         }
 
-        int ge = base;
+        // The run's groups are the 8-entry windows of `order` counted from `base`; the warps of the CTA draw them
+        // from a shared counter and never meet at a barrier inside the run, so their load, MMA and store phases
+        // drift apart and overlap.
         for (;;) {
-            // the group: up to eight consecutive entries of `order` that share the set (every warp derives it alike)
+            int k = 0;
+            if (lane == 0) k = atomicAdd(&sGrab, 1);
+            k = __shfl_sync(full, k, 0);
+            const int ge = base + kGroup * k;
+            if (ge >= e1) break;
             int my_t = 0;
             bool ok = false;
             if (lane < kGroup && ge + lane < e1) { my_t = A.order[ge + lane]; ok = A.param_id[my_t] == ps; }
             const unsigned m = __ballot_sync(full, ok) & 0xffu;
-            const int ng = __ffs(~m) - 1;       // leading run of valid entries, 0..8
-            if (ng == 0) break;
-            if (ng == kGroup) {                 // start the next group's coordinates on their way into L2
-                const int per = 3 * S / 16;     // 128-byte lines per tetrad
-                for (int line = tid; line < kGroup * per; line += kThreads) {
-                    const int u = line / per, o = line - u * per;
-                    const int en = ge + kGroup + u;
-                    if (en < e1) prefetch_l2(A.crd_in + (size_t)A.order[en] * 3 * S + o * 16);
+            const int ng = __ffs(~m) - 1;       // leading run of entries that share the set, 0..8
+            if (ng > 0) {
+                {   // the group's coordinates on their way into L2 (the loads below then see L2 latency, not HBM's)
+                    const int per = 3 * S / 16;  // 128-byte lines per tetrad
+                    for (int i0 = 0; i0 < kGroup * per; i0 += 32) {
+                        const int i = i0 + lane;
+                        const bool in = i < kGroup * per;
+                        const int u = in ? i / per : 0, o = i - u * per;
+                        const int tu = __shfl_sync(full, my_t, u);
+                        if (in && u < ng) prefetch_l2(A.crd_in + (size_t)tu * 3 * S + o * 16);
+                    }
                 }
-            }
-
-            // ---- pass 1: partial projections over this warp's 32 atoms
-            const int tg = __shfl_sync(full, my_t, g);
-            if (active) {
+                const int tg = __shfl_sync(full, my_t, g);
                 const bool colv = g < ng;
-                double R[9], ca[3], cx[3];
-#pragma unroll
-                for (int q = 0; q < 9; q++) R[q] = 0.0;
-#pragma unroll
-                for (int q = 0; q < 3; q++) ca[q] = cx[q] = 0.0;
-                const double* XIN = A.crd_in;
-                if (colv) {
-                    const double* SUP = A.sup + (size_t)tg * kSupW;
-#pragma unroll
-                    for (int q = 0; q < 9; q++) R[q] = SUP[q];
-#pragma unroll
-                    for (int q = 0; q < 3; q++) { ca[q] = SUP[12 + q]; cx[q] = SUP[15 + q]; }
-                    XIN = A.crd_in + (size_t)tg * 3 * S;
-                }
-                double x[8][3];
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    const int a = ab + 4 * s + r;
-                    x[s][0] = x[s][1] = x[s][2] = 0.0;
-                    if (colv && a < na) { x[s][0] = XIN[a]; x[s][1] = XIN[S + a]; x[s][2] = XIN[2 * S + a]; }
-                }
-                double acc[2][3][2];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) acc[mt][c][0] = acc[mt][c][1] = 0.0;
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    const int a = ab + 4 * s + r;
-                    double d[3] = {0.0, 0.0, 0.0};
-                    if (colv && a < na) {       // edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
-                        const double ac0 = sAV[a] - ca[0], ac1 = sAV[S + a] - ca[1], ac2 = sAV[2 * S + a] - ca[2];
-                        const double xc0 = x[s][0] - cx[0], xc1 = x[s][1] - cx[1], xc2 = x[s][2] - cx[2];
-                        d[0] = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
-                        d[1] = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
-                        d[2] = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {   // edmd.cpp:106-110: rows 0-7 and rows 8-11 (+ four zero rows) of E
-                        const double a_lo = sEV[g * SP + c * S + a];
-                        const double a_hi = g < 4 ? sEV[(8 + g) * SP + c * S + a] : 0.0;
-                        dmma(acc[0][c], a_lo, d[c]);
-                        dmma(acc[1][c], a_hi, d[c]);
-                    }
-                }
-                double* part = sPart + (size_t)(buf * kWarps + warp) * kPartRow;
-                {
-                    const double p0 = (acc[0][0][0] + acc[0][1][0]) + acc[0][2][0];
-                    const double p1 = (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1];
-                    *reinterpret_cast<double2*>(part + g * kGroup + 2 * r) = make_double2(p0, p1);
-                }
-                if (g < 4) {
-                    const double p0 = (acc[1][0][0] + acc[1][1][0]) + acc[1][2][0];
-                    const double p1 = (acc[1][0][1] + acc[1][1][1]) + acc[1][2][1];
-                    *reinterpret_cast<double2*>(part + (8 + g) * kGroup + 2 * r) = make_double2(p0, p1);
-                }
-            }
-            __syncthreads();
 
-            if (active) {
-                // ---- the projections of tetrad g on eigenvectors r, r + 4, r + 8: the B fragments of pass 2
-                double P[3], W[3], term[3];
+                // ---- pass 1: projections of the eight tetrads, K = all atoms, in 16-atom halves (loads one half ahead)
+                double acc[2][2];               // rows 0-7 / 8-11 of P: one accumulation chain each, in atom order
+                acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = 0.0;
                 {
-                    const double* pb = sPart + (size_t)buf * kWarps * kPartRow;
+                    double R[9], ca[3], cx[3];
 #pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        const int o = (r + 4 * q) * kGroup + g;
-                        double s = pb[o];
-                        for (int w = 1; w < nblk; w++) s += pb[w * kPartRow + o];
-                        P[q] = s;
-                        W[q] = -(s * A.scaled / el[q]);
-                        term[q] = s * s / el[q];
+                    for (int q = 0; q < 9; q++) R[q] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) ca[q] = cx[q] = 0.0;
+                    const double* XIN = A.crd_in;
+                    if (colv) {
+                        const double* SUP = A.sup + (size_t)tg * kSupW;
+#pragma unroll
+                        for (int q = 0; q < 9; q++) R[q] = SUP[q];
+#pragma unroll
+                        for (int q = 0; q < 3; q++) { ca[q] = SUP[12 + q]; cx[q] = SUP[15 + q]; }
+                        XIN = A.crd_in + (size_t)tg * 3 * S;
+                    }
+                    auto load_half = [&](double (&x)[4][3], int hb) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
+                            const int a = 16 * hb + 4 * s + r;
+                            x[s][0] = x[s][1] = x[s][2] = 0.0;
+                            if (colv && a < na) { x[s][0] = XIN[a]; x[s][1] = XIN[S + a]; x[s][2] = XIN[2 * S + a]; }
+                        }
+                    };
+                    auto compute_half = [&](const double (&x)[4][3], int hb) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
+                            const int a = 16 * hb + 4 * s + r;
+                            double d[3] = {0.0, 0.0, 0.0};
+                            if (colv && a < na) {   // edmd.cpp:89-94 (centred copies as qcprot.c:382-386)
+                                const double ac0 = sAV[a] - ca[0], ac1 = sAV[S + a] - ca[1], ac2 = sAV[2 * S + a] - ca[2];
+                                const double xc0 = x[s][0] - cx[0], xc1 = x[s][1] - cx[1], xc2 = x[s][2] - cx[2];
+                                d[0] = R[0] * xc0 + R[1] * xc1 + R[2] * xc2 - ac0;
+                                d[1] = R[3] * xc0 + R[4] * xc1 + R[5] * xc2 - ac1;
+                                d[2] = R[6] * xc0 + R[7] * xc1 + R[8] * xc2 - ac2;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 3; c++) {   // edmd.cpp:106-110: rows 0-7 and rows 8-11 (+ four zero rows) of E
+                                const double a_lo = sEV[g * SP + c * S + a];
+                                const double a_hi = g < 4 ? sEV[(8 + g) * SP + c * S + a] : 0.0;
+                                dmma(acc[0], a_lo, d[c]);
+                                dmma(acc[1], a_hi, d[c]);
+                            }
+                        }
+                    };
+                    double xA[4][3], xB[4][3];
+                    load_half(xA, 0);
+#pragma unroll 1
+                    for (int b = 0; b < nblk; b++) {
+                        load_half(xB, 2 * b + 1);
+                        compute_half(xA, 2 * b);
+                        if (b + 1 < nblk) load_half(xA, 2 * b + 2);
+                        compute_half(xB, 2 * b + 1);
                     }
                 }
-                if (warp == 0) {                // edmd.cpp:153-157, summed in eigenvector order
+                // D fragments (row = eigenvector g / 8 + g, columns = tetrads 2r, 2r + 1) -> B fragments of pass 2
+                __syncwarp();                   // the previous group's reads of the scratch are done
+                *reinterpret_cast<double2*>(sXp + g * kGroup + 2 * r) = make_double2(acc[0][0], acc[0][1]);
+                if (g < 4) *reinterpret_cast<double2*>(sXp + (8 + g) * kGroup + 2 * r) = make_double2(acc[1][0], acc[1][1]);
+                __syncwarp();
+                // the projections of tetrad g on eigenvectors r, r + 4, r + 8
+                double P[3], W[3], term[3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double s = sXp[(r + 4 * q) * kGroup + g];
+                    P[q] = s;
+                    W[q] = -(s * A.scaled / el[q]);
+                    term[q] = s * s / el[q];
+                }
+                {   // edmd.cpp:153-157, summed in eigenvector order
                     double en = 0.0;
 #pragma unroll
                     for (int j = 0; j < kRows; j++) {
                         const double v = __shfl_sync(full, term[j >> 2], (lane & ~3) | (j & 3));
                         if (j < nev) en += v;
                     }
-                    if (r == 0 && g < ng) A.e_ed[tg] = en * (0.5 * A.scaled);
+                    if (r == 0 && colv) A.e_ed[tg] = en * (0.5 * A.scaled);
                 }
 
                 // ---- pass 2: re-embedding and force (edmd.cpp:113-127), back to the laboratory frame (:130-150)
@@ -230,62 +232,67 @@ __global__ void __launch_bounds__(kThreads, 2) ed_project_mma_kernel(MmaArgs A) 
 #pragma unroll
                     for (int q = 0; q < 3; q++) shb[q] = SUP[9 + q];
                 }
+                double* const Xa = A.crd + (size_t)ta * 3 * S;
+                double* const Fa = A.fed + (size_t)ta * 3 * S;
+                double* const Xb = A.crd + (size_t)tb * 3 * S;
+                double* const Fb = A.fed + (size_t)tb * 3 * S;
+#pragma unroll 1
+                for (int b = 0; b < nblk; b++) {
 #pragma unroll
-                for (int tau = 0; tau < 4; tau++) {
-                    const int a = ab + 8 * tau + g;
-                    double sv[3][2], fv[3][2];
+                    for (int tau = 0; tau < 4; tau++) {
+                        const int a = 32 * b + 8 * tau + g;
+                        double sv[3][2], fv[3][2];
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        sv[c][0] = sv[c][1] = sAV[c * S + a];
-                        fv[c][0] = fv[c][1] = 0.0;
-                    }
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-#pragma unroll
-                        for (int q = 0; q < 3; q++) {
-                            const double ev = sEV[(4 * q + r) * SP + c * S + a];
-                            dmma(sv[c], ev, P[q]);
-                            dmma(fv[c], ev, W[q]);
+                        for (int c = 0; c < 3; c++) {
+                            sv[c][0] = sv[c][1] = sAV[c * S + a];
+                            fv[c][0] = fv[c][1] = 0.0;
                         }
-                    }
-                    if (a < na) {
-                        if (va) {
-                            const double s0 = sv[0][0] - sha[0], s1 = sv[1][0] - sha[1], s2 = sv[2][0] - sha[2];
-                            const double f0 = fv[0][0], f1 = fv[1][0], f2 = fv[2][0];
-                            double* X = A.crd + (size_t)ta * 3 * S;
-                            double* F = A.fed + (size_t)ta * 3 * S;
-                            X[a]         = Ra[0] * s0 + Ra[3] * s1 + Ra[6] * s2;
-                            X[S + a]     = Ra[1] * s0 + Ra[4] * s1 + Ra[7] * s2;
-                            X[2 * S + a] = Ra[2] * s0 + Ra[5] * s1 + Ra[8] * s2;
-                            F[a]         = Ra[0] * f0 + Ra[3] * f1 + Ra[6] * f2;
-                            F[S + a]     = Ra[1] * f0 + Ra[4] * f1 + Ra[7] * f2;
-                            F[2 * S + a] = Ra[2] * f0 + Ra[5] * f1 + Ra[8] * f2;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+#pragma unroll
+                            for (int q = 0; q < 3; q++) {
+                                const double ev = sEV[(4 * q + r) * SP + c * S + a];
+                                dmma(sv[c], ev, P[q]);
+                                dmma(fv[c], ev, W[q]);
+                            }
                         }
-                        if (vb) {
-                            const double s0 = sv[0][1] - shb[0], s1 = sv[1][1] - shb[1], s2 = sv[2][1] - shb[2];
-                            const double f0 = fv[0][1], f1 = fv[1][1], f2 = fv[2][1];
-                            double* X = A.crd + (size_t)tb * 3 * S;
-                            double* F = A.fed + (size_t)tb * 3 * S;
-                            X[a]         = Rb[0] * s0 + Rb[3] * s1 + Rb[6] * s2;
-                            X[S + a]     = Rb[1] * s0 + Rb[4] * s1 + Rb[7] * s2;
-                            X[2 * S + a] = Rb[2] * s0 + Rb[5] * s1 + Rb[8] * s2;
-                            F[a]         = Rb[0] * f0 + Rb[3] * f1 + Rb[6] * f2;
-                            F[S + a]     = Rb[1] * f0 + Rb[4] * f1 + Rb[7] * f2;
-                            F[2 * S + a] = Rb[2] * f0 + Rb[5] * f1 + Rb[8] * f2;
+                        if (a < na) {
+                            if (va) {
+                                const double s0 = sv[0][0] - sha[0], s1 = sv[1][0] - sha[1], s2 = sv[2][0] - sha[2];
+                                const double f0 = fv[0][0], f1 = fv[1][0], f2 = fv[2][0];
+                                Xa[a]         = Ra[0] * s0 + Ra[3] * s1 + Ra[6] * s2;
+                                Xa[S + a]     = Ra[1] * s0 + Ra[4] * s1 + Ra[7] * s2;
+                                Xa[2 * S + a] = Ra[2] * s0 + Ra[5] * s1 + Ra[8] * s2;
+                                Fa[a]         = Ra[0] * f0 + Ra[3] * f1 + Ra[6] * f2;
+                                Fa[S + a]     = Ra[1] * f0 + Ra[4] * f1 + Ra[7] * f2;
+                                Fa[2 * S + a] = Ra[2] * f0 + Ra[5] * f1 + Ra[8] * f2;
+                            }
+                            if (vb) {
+                                const double s0 = sv[0][1] - shb[0], s1 = sv[1][1] - shb[1], s2 = sv[2][1] - shb[2];
+                                const double f0 = fv[0][1], f1 = fv[1][1], f2 = fv[2][1];
+                                Xb[a]         = Rb[0] * s0 + Rb[3] * s1 + Rb[6] * s2;
+                                Xb[S + a]     = Rb[1] * s0 + Rb[4] * s1 + Rb[7] * s2;
+                                Xb[2 * S + a] = Rb[2] * s0 + Rb[5] * s1 + Rb[8] * s2;
+                                Fb[a]         = Rb[0] * f0 + Rb[3] * f1 + Rb[6] * f2;
+                                Fb[S + a]     = Rb[1] * f0 + Rb[4] * f1 + Rb[7] * f2;
+                                Fb[2 * S + a] = Rb[2] * f0 + Rb[5] * f1 + Rb[8] * f2;
+                            }
                         }
                     }
                 }
             }
-            ge += ng;
-            buf ^= 1;                           // the partials are double-buffered: one barrier per group suffices
-            if (ng < kGroup) break;             // the run (or the CTA's chunk) ends inside this group
+            if (ng < kGroup) {                  // the run (or the CTA's chunk) ends inside or before this window
+                if (lane == 0 && ge + ng < e1) atomicMin(&sNext, ge + ng);
+                break;
+            }
         }
-        base = ge;
-        if (base < e1) __syncthreads();         // every warp is done with this set's tables before the next set's arrive
+        __syncthreads();                        // every warp is done with this set's tables
+        base = __reduce_max_sync(full, sNext);
+        __syncthreads();                        // ... and has read sNext before thread 0 resets it
     }
 }
 
-size_t mma_smem_bytes(int S) { return sizeof(double) * ((size_t)kRows * (3 * S + 4) + 3 * S + 2 * kWarps * kPartRow); }
+size_t mma_smem_bytes(int S) { return sizeof(double) * ((size_t)kRows * (3 * S + 4) + 3 * S + kWarps * kPartRow); }
 
 }  // namespace
 

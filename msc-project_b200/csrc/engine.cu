@@ -420,7 +420,10 @@ int do_ed(edmd_engine* e) {
     const bool shared_sets = (long long)e->n >= 8LL * e->P;
     const bool warp = e->ed_kernel == 2 || (e->ed_kernel == 0 && shared_sets);
     // The tensor-core projection (ed_mma.cu) groups eight tetrads of one parameter set per MMA tile.
-    const bool mma = ed_project_mma_supported(e->ps) && (e->ed_kernel == 3 || (e->ed_kernel == 0 && shared_sets && e->ed_auto_mma));
+    // One warp carries a whole group there (no barrier inside a run), which needs a few thousand groups to fill the
+    // machine: small systems keep the warp-per-tetrad kernel.
+    const bool mma = ed_project_mma_supported(e->ps) &&
+                     (e->ed_kernel == 3 || (e->ed_kernel == 0 && shared_sets && e->ed_auto_mma && e->n >= 4096));
     timer_begin(e, T_SUP);
     CK(launch_superpose(e->ps, e->d_param_id, src, e->sup, e->t0, e->t1 - e->t0, e->sup_variant, e->sms, e->st));
     timer_end(e, T_SUP, 0);
