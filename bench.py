@@ -177,7 +177,48 @@ def config_dict(npairs):
             "inputs": "state planes 3.1 GB per GPU (> 126 MB L2): resident in HBM, nothing to flush between steps"}
 
 
-def cpu_sample(full, npairs_full, m, kind_wanted=None, reps=2, cache=None):
+def cpu_variants(pyoracle, o, full, npairs_full, m, np_sub, cores, kind, t_ed, t_rng, t_int):
+    """BASELINE.md section 3's other two CPU figures, each on a bounded sample: the same build on ONE core, and the build
+    at the optimisation level the reference ships with (-O0: its Makefile leaves CFLAGS empty) on all cores."""
+    out = {}
+    try:
+        p1 = max(1, np_sub // cores)                       # one thread's share of the sample's pair list
+        o.build_pairs()
+        t_nb1 = o.time_nb(0, p1, 1)
+        o.set_pairs([])
+        step1 = (t_ed + t_rng + t_int) * (full.n / m) + t_nb1 * (npairs_full / p1)
+        out["one_core"] = {"value": npairs_full / step1, "unit": UNIT, "cores": 1, "kind": kind, "ms_per_step": step1 * 1e3,
+                           "sample": f"NB on the first {p1} tetrad pairs of the sample, 1 thread: {t_nb1:.3f} s; ED, random terms "
+                                     f"and update as measured above, not divided"}
+    except Exception as ex:                                # a variant must never cost the bench line
+        out["one_core"] = {"error": repr(ex)}
+    try:
+        k0 = "reference_O0"
+        if kind == "reference" and pyoracle.available(k0):
+            m0 = max(200, m // 8)
+            sub0 = full.subset(range(m0))
+            o0 = pyoracle.Oracle(sub0, k0)
+            o0.set_time(RNG_TIME0)
+            np0 = o0.build_pairs()
+            t_nb0 = o0.time_nb(0, np0, cores)
+            o0.set_pairs([])
+            t0 = time.perf_counter(); o0.ed_forces(); t_ed0 = time.perf_counter() - t0
+            t0 = time.perf_counter(); o0.random_terms(); t_rng0 = time.perf_counter() - t0
+            t0 = time.perf_counter(); o0.update_velocities(); o0.update_coordinates(); t_int0 = time.perf_counter() - t0
+            o0.close()
+            step0 = ((t_ed0 + t_rng0) / cores + t_int0) * (full.n / m0) + t_nb0 * (npairs_full / np0)
+            out["shipped_O0"] = {"value": npairs_full / step0, "unit": UNIT, "cores": cores, "kind": "reference, g++ -O0 (the "
+                                 "reference's Makefile sets no optimisation flag)", "ms_per_step": step0 * 1e3,
+                                 "sample": f"first {m0} tetrads ({np0} pairs): NB {t_nb0:.3f} s on {cores} threads, ED {t_ed0:.3f} s, "
+                                           f"random terms {t_rng0:.3f} s (1 thread, counted /{cores}), update {t_int0:.3f} s serial"}
+        else:
+            out["shipped_O0"] = {"unavailable": "oracle/_ref/libedmd_ref_O0.so is built only where /root/reference exists"}
+    except Exception as ex:
+        out["shipped_O0"] = {"error": repr(ex)}
+    return out
+
+
+def cpu_sample(full, npairs_full, m, kind_wanted=None, reps=2, cache=None, with_variants=False):
     """The reference CPU path on a bounded sample of C3: the first `m` tetrads of the ring (a chain segment with
     its own cutoff pair list), all host threads.  Per-tetrad and per-pair costs are uniform along the ring, so the
     full step is assembled as  t_tetrad_part * n/m + t_nb * pairs/pairs_sample.  The step is modelled the way the
@@ -209,9 +250,12 @@ def cpu_sample(full, npairs_full, m, kind_wanted=None, reps=2, cache=None):
     t0 = time.perf_counter(); o.update_velocities(); o.update_coordinates(); t_int = time.perf_counter() - t0
     scale_t, scale_p = full.n / m, npairs_full / np_sub
     step_s = ((t_ed + t_rng) / cores + t_int) * scale_t + t_nb * scale_p
+    variants = None
+    if with_variants:
+        variants = cpu_variants(pyoracle, o, full, npairs_full, m, np_sub, cores, kind, t_ed, t_rng, t_int)
     if cache is None:
         o.close()
-    return {"value": npairs_full / step_s, "unit": UNIT, "cores": cores, "kind": kind,
+    return {"value": npairs_full / step_s, "unit": UNIT, "cores": cores, "kind": kind, "variants": variants,
             "sample": f"first {m} of {full.n} tetrads ({np_sub} of {npairs_full} tetrad pairs): NB {t_nb:.3f} s on {cores} threads; "
                       f"ED {t_ed:.3f} s and random terms {t_rng:.3f} s measured on 1 thread and counted /{cores} (perfectly "
                       f"parallel worker blocks, one libc stream per MPI worker); velocity+coordinate update {t_int:.3f} s serial "
@@ -344,6 +388,24 @@ def extra_contact(pkg, local, peak_tf):
                                             "evaluated atom pair + ~25 per pair inside atom_Cutoff; FP64-pipe activity from ncu "
                                             "is in profiles/"}
     return out
+
+
+def extra_c2(pkg, local):
+    """BASELINE configs[2]: 10,000-tetrad ring, shipped cutoffs, Langevin random forces on (1 GPU here)."""
+    s = pkg.make_ring(10000, kind="ring")
+    g = pkg.Engine(s, device=local)
+    g.set_rng(RNG_TIME0, 1, 0)
+    npairs = g.build_pairlist()
+    crd0, vel0 = s.crd.copy(), s.vel.copy()
+    g.step(5, 1); g.sync()
+    g.set_state(crd0, vel0)
+    ms = timed_steps(g, lambda r: g.step(r, 1), 100, 0)
+    g.set_state(crd0, vel0)
+    ph = phase_times(g, lambda r: g.step(r, 1), 5)
+    g.close()
+    return {"workload": "C2: synthetic 10000-tetrad replicated GC DNA ring, cutoff pair list, Langevin random forces on, 1 GPU",
+            "tetrads": s.n, "tetrad_pairs": npairs, "ms_per_step": ms, "value": npairs / (ms * 1e-3), "unit": UNIT,
+            "steps_per_sec": 1e3 / ms, "kernel_ms": ph}
 
 
 def multi_gpu_parity(pkg, dmod, dist, torch, rank, world, local):
@@ -510,6 +572,10 @@ def main():
     if world == 1 and not args.no_extras:
         extras["c1"] = extra_c1(pkg, eng_mod, local, peak_tf)
         extras["contact"] = extra_contact(pkg, local, peak_tf)
+        try:
+            extras["c2"] = extra_c2(pkg, local)
+        except Exception as ex:          # an extra must never cost the bench line
+            extras["c2"] = {"error": repr(ex)}
 
     if rank == 0:
         try:
@@ -564,7 +630,7 @@ def main():
         if extras:
             line["extras"] = extras
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_sample(s, npairs, args.cpu_sample)
+            line["cpu_baseline"] = cpu_sample(s, npairs, args.cpu_sample, with_variants=True)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -154,7 +154,7 @@ struct edmd_engine {
     long calls = 0;
 
     int ed_kernel = 0;   // projection kernel: 0 automatic, 1 thread-per-atom, 2 warp-per-tetrad, 3 tensor-core (edmd_set_ed_kernel)
-    bool ed_auto_mma = false;   // what "automatic" picks for shared parameter sets with <= 12 eigenvectors (EDMD_ED_MMA)
+    bool ed_auto_mma = true;    // "automatic" picks the tensor-core projection for large systems with shared sets (EDMD_ED_MMA=0: never)
     int cull_dense_min = 9;   // sphere masks with this many blocks or more go to the tiled distance kernel (EDMD_CULL_DENSE)
     int sup_variant = 0; // superposition kernel: 0 by size, 1 one tetrad per warp, 2 two tetrads per warp (EDMD_SUPERPOSE)
     int scan_mode = 4;   // 0 direct, 1 gram, 2 fp32 prefilter, 4 gram + culling (default; see nb.cu)

@@ -24,7 +24,8 @@ PI = C.POINTER(C.c_int)
 LL = C.c_longlong
 
 PATHS = {"port": os.path.join(_HERE, "_build", "libedmd_oracle.so"),
-         "reference": os.path.join(_HERE, "_ref", "libedmd_ref.so")}
+         "reference": os.path.join(_HERE, "_ref", "libedmd_ref.so"),
+         "reference_O0": os.path.join(_HERE, "_ref", "libedmd_ref_O0.so")}   # same sources at the shipped -O0 (timing only)
 _LIBS = {}
 
 
@@ -34,7 +35,7 @@ def available(kind: str) -> bool:
 
 def build(kind: str = "port", ref_root: str = "/root/reference") -> bool:
     target = "port" if kind == "port" else "ref"
-    if kind == "reference" and not os.path.isdir(ref_root):
+    if kind != "port" and not os.path.isdir(ref_root):
         return available(kind)
     subprocess.run(["make", "-C", _HERE, target, f"REF={ref_root}"], check=True,
                    stdout=subprocess.DEVNULL)

@@ -209,21 +209,46 @@ def test_step_host_matches_the_three_separate_calls(edmd, ragged):
 
 
 def test_both_projection_kernels_match_the_oracle(edmd, po):
-    """ED pass with the thread-per-atom projection (edmd_set_ed_kernel(1)) and with the warp-per-tetrad
-    projection (2) on a system whose tetrads share two parameter sets and on one where every tetrad has
-    its own: both within the parity bound of the CPU oracle, and equal to each other up to the order of
-    the 12 projection sums."""
+    """ED pass with the thread-per-atom projection (edmd_set_ed_kernel(1)), the warp-per-tetrad projection (2)
+    and the tensor-core projection (3, DMMA over groups of eight tetrads) on a system whose tetrads share
+    parameter sets and on one where every tetrad has its own (groups of one): all within the parity bound
+    of the CPU oracle, and equal to each other up to the order of the 12 projection sums."""
     for s in (edmd.make_ring(120, kind="coil", laps=3, lap_gap=9.0), edmd.make_gc90()):
         o = po.Oracle(s, "port"); o.build_pairs(); o.forces(random_on=False)
         fo = o.get_forces(); co, _ = o.get_state()
         out = []
-        for which in (1, 2, 0):
+        for which in (1, 2, 3, 0):
             g = edmd.Engine(s); g.set_ed_kernel(which); g.build_pairlist(); g.ed_forces()
             fg = g.get_forces(); cg, _ = g.get_state()
             assert rel(fg["ed"], fo["ed"]) < TOL and rel(fg["ed_energy"], fo["ed_energy"]) < TOL
             assert rel(cg, co) < TOL
             out.append((fg["ed"], cg))
         assert rel(out[0][0], out[1][0]) < 1e-12 and rel(out[0][1], out[1][1]) < 1e-13
+        assert rel(out[0][0], out[2][0]) < 1e-12 and rel(out[0][1], out[2][1]) < 1e-13
+
+
+def test_tensor_core_projection_is_independent_of_the_grouping(edmd):
+    """The tensor-core projection puts eight tetrads of one parameter set into the columns of an MMA tile.  A
+    tetrad's result must not depend on which tetrads share its tile (that is what keeps multi-GPU runs
+    bit-identical to one GPU): a shard that starts three tetrads later regroups every tile.  Also: 4,100 tetrads
+    with shared sets is a system for which 'automatic' picks this kernel."""
+    s = edmd.make_ring(4100, kind="ring")
+    n, w = s.n, 3 * 252
+    res = []
+    for which, shard in ((3, None), (3, (3, n - 5)), (0, None), (2, None)):
+        g = edmd.Engine(s); g.set_ed_kernel(which)
+        npairs = g.build_pairlist()
+        if shard is not None:
+            g.set_shard(shard[0], shard[1], 0, npairs)
+        g.ed_forces()
+        f = g.get_forces(); c, _ = g.get_state()
+        res.append((f["ed"].reshape(n, w), f["ed_energy"].copy(), c.reshape(n, w)))
+        g.close()
+    full, part, auto, warp = res
+    assert np.array_equal(full[0][3:n - 5], part[0][3:n - 5]) and np.array_equal(full[2][3:n - 5], part[2][3:n - 5])
+    assert np.array_equal(full[1][3:n - 5], part[1][3:n - 5])
+    assert np.array_equal(full[0], auto[0]) and np.array_equal(full[2], auto[2])
+    assert rel(full[0], warp[0]) < 1e-12 and rel(full[2], warp[2]) < 1e-13 and rel(full[1], warp[1]) < 1e-12
 
 
 def test_small_atom_stride_system(edmd, po):

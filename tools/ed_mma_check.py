@@ -55,7 +55,10 @@ def small_cases():
 def big_case(n):
     s = pkg.make_ring(n, kind="ring")
     res = {}
-    for which in (2, 3):
+    variants = [(2, None)] + [(3, m) for m in os.environ.get("CHECK_PREFETCH_MODES", "1").split(",")]
+    for which, pf in variants:
+        if pf is not None:
+            os.environ["EDMD_ED_MMA_PREFETCH"] = pf
         g = pkg.Engine(s); g.set_ed_kernel(which); g.set_rng(1000000000, 1, 0)
         npairs = g.build_pairlist()
         g.ed_forces()
@@ -72,7 +75,7 @@ def big_case(n):
         g.step(5, 1); g.sync()
         g.mark(0); g.step(50, 1); g.mark(1)
         step_ms = g.mark_elapsed(0, 1) / 50
-        out(case=f"ring{n}", kernel=which, pairs=npairs, ed_ms=ed_ms, superpose_ms=sup_ms, project_ms=ed_ms - sup_ms,
+        out(case=f"ring{n}", kernel=which, prefetch=pf, pairs=npairs, ed_ms=ed_ms, superpose_ms=sup_ms, project_ms=ed_ms - sup_ms,
             step_ms_random_on=step_ms)
         g.close()
     out(case=f"ring{n}", k3_vs_k2=dict(ed=rel(res[3][0], res[2][0]), e_ed=rel(res[3][1], res[2][1]), crd=rel(res[3][2], res[2][2])),
