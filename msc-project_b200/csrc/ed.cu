@@ -21,6 +21,9 @@
 //    shift of a tetrad's coordinates (1e-14 A instead of 1e-17) is amplified by the cancellation in
 //    clashing electrostatic contacts to 4e-10 on NB forces: over the parity bound, dropped.)
 //
+//  (Large systems whose tetrads share parameter sets with <= 12 eigenvectors use ed_project_mma_kernel, ed_mma.cu: the
+//  same two passes as FP64 tensor-core contractions over groups of eight tetrads.  The two kernels below serve small
+//  systems, sets with more eigenvectors and edmd_set_ed_kernel(1|2).)
 //  ed_project_warp_kernel (parameter sets with <= 12 eigenvectors: one warp per tetrad, the set's
 //    eigenvectors staged in shared memory once per run of tetrads) and ed_project_kernel (any
 //    number of eigenvectors: 256 threads per tetrad, thread a <-> atom a, coefficients in

@@ -11,23 +11,29 @@
 // coefficient of E from shared memory once per pass and tetrad: 147 KB = 1,390 shared-memory wavefronts per
 // tetrad, which is what bounds it (profiles/ncu_r02_c3_step_details.txt).  Here T = 8 tetrads form the N
 // dimension of mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), so a coefficient fetched from shared memory is used for eight
-// tetrads: 84 + 72 shared-memory loads per lane and tetrad group instead of 8 x 576.
+// tetrads: 25 M shared-memory wavefronts per launch at 1e5 tetrads instead of 139 M (ncu).
 //
-// One CTA (8 warps) walks a run of tetrads that share a parameter set, eight at a time:
-//   pass 1   warp w owns atoms 32w..32w+31 (the K range of the contraction): lane (g = lane/4, r = lane%4) loads
-//            atom 32w + 4s + r of tetrad g, s = 0..7, forms its displacement with the reference's expressions and
-//            feeds it as the B fragment of six DMMAs per s (3 planes x rows 0-7 / 8-11 of E); the A fragments come
-//            from the staged E, whose row stride 3S + 4 doubles makes both passes' fragment loads conflict-free.
-//            The warp's partial P goes to shared memory; after ONE CTA barrier every warp adds the eight partials
-//            in warp order (fixed order: bit-stable, independent of how tetrads are grouped).
-//   pass 2   warp w owns the same 32 atoms as four 8-atom M tiles; K = the 12 eigenvectors in three steps; the
-//            accumulators start from avg (S') and 0 (F'); the D fragment leaves lane (g, r) with atom 8 tau + g of
-//            tetrads 2r and 2r + 1, all three components, which it rotates back to the laboratory frame
-//            (edmd.cpp:130-150) and stores.
+// A CTA (8 warps, 2 CTAs per SM) stages one parameter set's E (row stride 3S + 4 doubles: both passes' fragment
+// loads are conflict-free) and average structure once per run of tetrads that share the set.  Inside the run every
+// WARP carries whole groups of eight tetrads, drawn from a shared counter; the warps never meet at a barrier, so
+// their load, MMA and store phases drift apart and overlap.  (A CTA-cooperative form — eight warps split one group's
+// K range and meet at a barrier per group — measured 0.572 ms at 1e5 tetrads against 0.49-0.50 for this one.)
+//   pass 1   K = all atoms, four at a time: lane (g = lane/4, r = lane%4) loads atom 4s + r of tetrad g (one
+//            16-atom half ahead of its use), forms its displacement with the reference's expressions and feeds it
+//            as the B fragment of six DMMAs per s (3 planes x rows 0-7 / 8-11 of E).  Two accumulation chains (one
+//            per row tile) in atom order: a fixed order, bit-stable.
+//   transposition   the D fragments (row = eigenvector, columns = tetrads 2r, 2r + 1) go through a 768-byte per-warp
+//            scratch and come back as pass 2's B fragments (projections of tetrad g on eigenvectors r, r + 4, r + 8);
+//            the ED energy is summed in eigenvector order (edmd.cpp:153-157).
+//   pass 2   8-atom M tiles; K = the 12 eigenvectors in three steps; the accumulators start from avg (S') and 0 (F');
+//            the D fragment leaves lane (g, r) with atom 8 tau + g of tetrads 2r and 2r + 1, all three components,
+//            which it rotates back to the laboratory frame (edmd.cpp:130-150) and stores.
 // Every column of an MMA is computed independently of the others, so a tetrad's result does not depend on which
-// other tetrads share its group: the results are identical for every shard layout / number of GPUs.
-// Same arithmetic as the other projection kernels up to the order of the twelve projection sums (~1e-16).
+// other tetrads share its group: the results are identical for every shard layout / number of GPUs (GPU-tested).
+// Same arithmetic as the other projection kernels up to the order of the twelve projection sums (~1e-15).
 // Compiled with -fmad=false like ed.cu (the displacement and the back-rotation round like the CPU build).
+// Measured (ncu, profiles/ncu_r02_ed_project_mma_details.txt): 0.50 ms at 1e5 tetrads; DMMA pipe 38 % + FP64 pipe 18 %
+// active; DRAM traffic = the compulsory 18.6 KB per tetrad at 3.6 TB/s; a third of the warp time waits on coordinate loads.
 #include "common.cuh"
 #include "kernels.h"
 #include <stdlib.h>

@@ -83,3 +83,28 @@ def test_ring_pair_count_equals_the_oracle_list():
         s = pkg.make_ring(n, kind="ring")
         o = pyoracle.Oracle(s, "port")
         assert o.build_pairs() == bench.ring_pair_count(s)
+
+
+def test_cpu_baseline_variants():
+    """The GPU arm's cpu_baseline also reports BASELINE.md section 3's other two CPU figures — one core, and the
+    reference at the -O0 it ships with — each on a bounded sample; a failing variant yields an error entry, never
+    an exception (it must not cost the bench line)."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import importlib
+    import pyoracle
+    bench = importlib.import_module("bench")
+    pkg = importlib.import_module("msc-project_b200")
+    s = pkg.make_ring(2000, kind="ring")
+    npairs = bench.ring_pair_count(s)
+    kind = "reference" if pyoracle.available("reference") else "port"
+    r = bench.cpu_sample(s, npairs, 1600, kind_wanted=kind, reps=1, with_variants=True)
+    assert r["value"] > 0 and r["kind"] == kind
+    v = r["variants"]
+    one = v["one_core"]
+    assert one["cores"] == 1 and 0 < one["value"] <= r["value"] * 1.5
+    o0 = v["shipped_O0"]
+    if kind == "reference" and pyoracle.available("reference_O0"):
+        assert o0["cores"] == r["cores"] and 0 < o0["value"] < r["value"]      # -O0 is slower than -O3
+    else:
+        assert "unavailable" in o0
+    assert bench.cpu_sample(s, npairs, 1600, kind_wanted=kind, reps=1)["variants"] is None
