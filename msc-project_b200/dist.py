@@ -15,8 +15,9 @@ only its shard:
 
   * tetrads are split into contiguous equal blocks (owner of a tetrad runs its ED force, random
     term, NB accumulation + clip, velocity and coordinate update);
-  * the flat tetrad-pair list is split into contiguous equal slices for the FP64 distance pass
-    (the reference's NB_Index split, master.cpp:225-239).
+  * the flat tetrad-pair list is split into contiguous slices for the FP64 distance pass (the reference's
+    NB_Index split, master.cpp:225-239): equal counts, or equal total weight when the caller passes per-pair
+    work estimates (``pair_weights``).
 
 Small systems (n <= REPLICATE_MAX_TETRADS) skip the first exchange: the per-tetrad kernels cost
 ~50 ns per tetrad while an all-gather costs ~50 us of latency, so every rank runs ED / accumulate /
@@ -54,15 +55,35 @@ def block_range(total: int, world: int, rank: int):
 
 
 class ShardPlan:
-    def __init__(self, n_tetrads: int, n_pairs: int, world: int, rank: int):
+    """Contiguous tetrad blocks and contiguous slices of the pair list (replaces generate_Indexes, master.cpp:214-242).
+    Pair slices hold equal COUNTS by default; with ``pair_weights`` (one non-negative work estimate per listed
+    pair, the same array on every rank) they hold equal total WEIGHT instead — the distance pass of a culled pair
+    costs a sphere test, that of a pair in contact up to 64 atom blocks.  Any slicing gives the same result bits:
+    a pair's block mask does not depend on which rank computes it."""
+
+    def __init__(self, n_tetrads: int, n_pairs: int, world: int, rank: int, pair_weights=None):
         self.n, self.np, self.world, self.rank = n_tetrads, n_pairs, world, rank
         self.t0, self.t1, self.t_chunk = block_range(n_tetrads, world, rank)
         self.p0, self.p1, self.p_chunk = block_range(n_pairs, world, rank)
+        self.p_bounds = None
+        if pair_weights is not None and n_pairs > 0 and world > 1:
+            w = np.asarray(pair_weights, dtype=np.float64).reshape(-1)
+            if w.shape[0] != n_pairs or not np.all(np.isfinite(w)) or np.any(w < 0):
+                raise ValueError("pair_weights: one finite non-negative value per listed pair")
+            c = np.cumsum(w)
+            if c[-1] > 0:
+                # slice r ends with the first pair at which the running weight reaches (r + 1) / world of the total
+                cuts = np.searchsorted(c, c[-1] * np.arange(1, world) / world, side="left") + 1
+                b = np.concatenate([[0], np.minimum(cuts, n_pairs), [n_pairs]]).astype(np.int64)
+                self.p_bounds = np.maximum.accumulate(b)
+                self.p0, self.p1 = int(self.p_bounds[rank]), int(self.p_bounds[rank + 1])
 
     def tetrad_range(self, r):
         return block_range(self.n, self.world, r)[:2]
 
     def pair_range(self, r):
+        if self.p_bounds is not None:
+            return int(self.p_bounds[r]), int(self.p_bounds[r + 1])
         return block_range(self.np, self.world, r)[:2]
 
     @property
@@ -71,7 +92,7 @@ class ShardPlan:
 
     @property
     def even_pairs(self):
-        return self.np == self.p_chunk * self.world
+        return self.p_bounds is None and self.np == self.p_chunk * self.world
 
 
 class HaloPlan:
@@ -196,8 +217,11 @@ class ShardedEngine:
     """Runs the reference step protocol (simulation.cpp:34-55) over world_size ranks."""
 
     def __init__(self, backend, dist, n_tetrads: int, rank: int, world: int, group=None, replicate=None,
-                 halo=None, native=None):
+                 halo=None, native=None, pair_weights=None):
         self.b, self.dist, self.n, self.rank, self.world, self.group = backend, dist, n_tetrads, rank, world, group
+        # per-pair work estimates for ShardPlan: None (equal counts), an array, or a function of the pair list
+        # ([np, 2] int array) evaluated after every rebuild — it must return the same values on every rank
+        self.pair_weights = pair_weights
         # native: the engine itself runs the sharded step over peer memory (GPU engine, world > 1)
         self.native = (hasattr(backend, "peer_export") and world > 1) if native is None else bool(native)
         if replicate is None:
@@ -212,11 +236,12 @@ class ShardedEngine:
         self.time0, self.rng_rank, self.calls = 1000000000, 1, 0
 
     # -- collectives -------------------------------------------------------------------
-    def _all_gather_blocks(self, flat, elems_per_unit, total_units, chunk_units):
-        """In-place all-gather of contiguous per-rank blocks of `flat` (a 1-D tensor)."""
+    def _all_gather_blocks(self, flat, elems_per_unit, total_units, chunk_units, ranges=None):
+        """In-place all-gather of contiguous per-rank blocks of `flat` (a 1-D tensor): equal blocks of
+        `chunk_units`, or the explicit per-rank `ranges` [(lo, hi)] of a weighted plan."""
         if self.world == 1:
             return
-        even = total_units == chunk_units * self.world
+        even = ranges is None and total_units == chunk_units * self.world
         lo, hi, _ = block_range(total_units, self.world, self.rank)
         if even:
             mine = flat[lo * elems_per_unit: hi * elems_per_unit]
@@ -224,7 +249,7 @@ class ShardedEngine:
         else:
             parts = []
             for r in range(self.world):
-                a, b, _ = block_range(total_units, self.world, r)
+                a, b = ranges[r] if ranges is not None else block_range(total_units, self.world, r)[:2]
                 parts.append(flat[a * elems_per_unit: b * elems_per_unit])
             # uneven blocks: one broadcast per non-empty block
             for r, part in enumerate(parts):
@@ -252,7 +277,16 @@ class ShardedEngine:
         self._all_gather_blocks(self.b.vel_tensor(), self.b.plane_elems, self.n, self.plan_t_chunk)
 
     def gather_hits(self):
-        self._all_gather_blocks(self.b.hit_tensor(), 1, self.plan.np, self.plan.p_chunk)
+        ranges = None
+        if self.plan.p_bounds is not None:
+            ranges = [self.plan.pair_range(r) for r in range(self.world)]
+        self._all_gather_blocks(self.b.hit_tensor(), 1, self.plan.np, self.plan.p_chunk, ranges)
+
+    def _make_plan(self, npairs):
+        w = self.pair_weights
+        if callable(w):
+            w = w(self.b.get_pairlist()) if npairs > 0 else None
+        return ShardPlan(self.n, npairs, self.world, self.rank, pair_weights=w)
 
     @property
     def plan_t_chunk(self):
@@ -266,7 +300,7 @@ class ShardedEngine:
             return self._build_native()
         self.b.set_shard(0, self.n, 0, 0)
         npairs = self.b.build_pairlist()
-        self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
+        self.plan = self._make_plan(npairs)
         if self.replicate:
             self.plan.t0, self.plan.t1 = 0, self.n
         self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)
@@ -309,7 +343,7 @@ class ShardedEngine:
             npairs = self.b.build_pairlist()
         if not self._attached:
             self._attach()
-        self.plan = ShardPlan(self.n, npairs, self.world, self.rank)
+        self.plan = self._make_plan(npairs)
         if self.replicate:
             self.plan.t0, self.plan.t1 = 0, self.n
         self.b.set_shard(self.plan.t0, self.plan.t1, self.plan.p0, self.plan.p1)

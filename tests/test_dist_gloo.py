@@ -110,7 +110,12 @@ class OracleBackend:
     def sync(self): pass
 
 
-def _worker(rank, world, port, q, replicate, halo=False, n_tet=30):
+def _skewed_weights(pairs):
+    """Pairs that touch the first ten tetrads count fifty-fold (a stand-in for pairs in contact)."""
+    return 1.0 + 49.0 * ((pairs[:, 0] < 10) | (pairs[:, 1] < 10))
+
+
+def _worker(rank, world, port, q, replicate, halo=False, n_tet=30, weighted=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle as po
     pkg = importlib.import_module("msc-project_b200")
@@ -119,7 +124,8 @@ def _worker(rank, world, port, q, replicate, halo=False, n_tet=30):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     system = pkg.make_ring(n_tet, kind="coil", laps=2, lap_gap=9.0)
     b = OracleBackend(po, system)
-    sh = dmod.ShardedEngine(b, dist, system.n, rank, world, replicate=replicate, halo=halo)
+    sh = dmod.ShardedEngine(b, dist, system.n, rank, world, replicate=replicate, halo=halo,
+                            pair_weights=_skewed_weights if weighted else None)
     npairs = sh.build_pairlist()
     sh.step(2, 0)
     sh.merge()
@@ -186,6 +192,57 @@ def test_halo_exchange_equals_single_rank(edmd, po, world):
     co, vo = o.get_state()
     assert np.array_equal(c, co) and np.array_equal(v, vo)
     assert 0 < halo_rows < system.n          # a real, partial halo
+
+
+def test_weighted_pair_slices_equal_single_rank(edmd, po):
+    """Pair slices of equal WEIGHT instead of equal count (world 3, skewed weights): the slices differ from the
+    default plan's, the hit flags travel as uneven blocks, and the result is still the single-rank result bit for bit."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 40
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, False, True, 40, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    npairs, c, v, plan, halo_rows = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    system = edmd.make_ring(40, kind="coil", laps=2, lap_gap=9.0)
+    o = po.Oracle(system, "port")
+    assert o.build_pairs() == npairs
+    dmod = importlib.import_module("msc-project_b200.dist")
+    pairs = o.get_pairs()
+    want = dmod.ShardPlan(system.n, npairs, world, 0, pair_weights=_skewed_weights(pairs))
+    assert plan == (want.t0, want.t1, want.p0, want.p1)
+    assert (want.p0, want.p1) != dmod.ShardPlan(system.n, npairs, world, 0).pair_range(0)
+    o.step(2); o.merge()
+    co, vo = o.get_state()
+    assert np.array_equal(c, co) and np.array_equal(v, vo)
+
+
+def test_weighted_shard_plan_balances_weight():
+    dmod = importlib.import_module("msc-project_b200.dist")
+    rng = np.random.default_rng(5)
+    for npairs, world in ((1000, 8), (37, 3), (5, 8), (400005, 8)):
+        w = rng.uniform(0.0, 1.0, npairs) ** 8 * 64 + 1.0          # a few heavy pairs among many light ones
+        seen = np.zeros(npairs, int)
+        sums = []
+        for r in range(world):
+            pl = dmod.ShardPlan(100, npairs, world, r, pair_weights=w)
+            assert (pl.p0, pl.p1) == pl.pair_range(r) and not pl.even_pairs
+            seen[pl.p0:pl.p1] += 1
+            sums.append(w[pl.p0:pl.p1].sum())
+        assert np.all(seen == 1)
+        assert max(sums) <= w.sum() / world + w.max() + 1e-9       # no slice exceeds its share by more than one pair
+    # all-zero weights, no weights, one rank: the equal-count plan
+    for kw in (dict(pair_weights=np.zeros(10)), dict()):
+        pl = dmod.ShardPlan(100, 10, 2, 1, **kw)
+        assert (pl.p0, pl.p1) == (5, 10) and pl.p_bounds is None
+    with pytest.raises(ValueError):
+        dmod.ShardPlan(100, 10, 2, 0, pair_weights=np.ones(9))
+    with pytest.raises(ValueError):
+        dmod.ShardPlan(100, 10, 2, 0, pair_weights=-np.ones(10))
 
 
 def test_halo_plan_lists(edmd):
